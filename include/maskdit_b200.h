@@ -1,0 +1,187 @@
+/* maskdit_b200 — C ABI of the B200 (sm_100a) MaskDiT hot path.
+ *
+ * The reference (Anima-Lab/MaskDiT) is pure Python/PyTorch and has no FFI layer; its seam for this path is the
+ * Python registries `Precond_models`, `DiT_models` (models/maskdit.py:709-715,779-781), `Losses`
+ * (train_utils/loss.py:66-68) and `edm_sampler` (sample.py:30-66).  The Python shim in `maskdit_b200/` implements
+ * those registries and calls the functions below through ctypes.  Every function:
+ *   - takes raw DEVICE pointers + sizes + a `cudaStream_t` (passed as void*), no torch types;
+ *   - is asynchronous on that stream, allocates nothing, frees nothing (caller owns all buffers);
+ *   - returns MDT_OK (0) or a negative MDT_ERR_* code; the shim raises on non-zero.
+ * Each declaration cites the reference code (file:line in /root/reference) whose arithmetic it replaces.
+ */
+#ifndef MASKDIT_B200_H_
+#define MASKDIT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDT_OK 0
+#define MDT_ERR_ARG (-1)    /* bad shape / alignment / null pointer */
+#define MDT_ERR_CUDA (-2)   /* launch failed; see cudaGetLastError */
+#define MDT_ERR_DRIVER (-3) /* cuTensorMapEncodeTiled entry point unavailable */
+#define MDT_ERR_TMAP (-4)   /* tensor-map encode rejected the operand */
+#define MDT_ERR_UNSUPPORTED (-5)
+
+const char* mdt_status_string(int status);
+int mdt_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * bf16 tensor-core GEMM (tcgen05 / TMEM / TMA):  out[M,N] (+)= sum_k A[m,k] * B[n,k], fp32 accumulate.
+ * Replaces every nn.Linear forward and its autograd dgrad/wgrad: timm Attention.qkv/proj and Mlp.fc1/fc2
+ * (ctor sites models/maskdit.py:178,182), adaLN_modulation (:185,206,227), DecoderLayer.linear (:203),
+ * FinalLayer.linear (:224), TimestepEmbedder.mlp (:34-38), LabelEmbedder.embedding_table (:75).
+ *   a_mn / b_mn = 0: operand stored [rows, K] with K contiguous ("K-major", row stride lda/ldb elements)
+ *               = 1: operand stored [K, rows] with rows contiguous ("MN-major")
+ * ------------------------------------------------------------------------------------------------------------ */
+enum { MDT_EPI_STORE = 0,      /* out = act(acc + bias [+ resid])            out bf16 or fp32            */
+       MDT_EPI_GELU = 1,       /* aux = bf16(acc+bias); out = bf16(gelu_tanh(aux))      (Mlp.fc1 + act)   */
+       MDT_EPI_GATE_RESID = 2, /* y = acc+bias; aux = bf16(y) (optional); out_f32 = resid + gate[row/rpg]*y
+                                  (DiTBlock residual update, models/maskdit.py:190-191)                   */
+       MDT_EPI_DGELU = 3,      /* out = bf16(acc * gelu_tanh'(aux))          (backward through GELU)      */
+       MDT_EPI_ATOMIC = 4 };   /* out_f32 += acc via red.global.add, stream-K schedule (wgrad, long-K)    */
+enum { MDT_ACT_NONE = 0, MDT_ACT_SILU = 1 };
+
+typedef struct mdt_gemm_args {
+  const void* A; /* bf16 */
+  const void* B; /* bf16 */
+  int M, N, K;
+  int lda, ldb;  /* row strides in elements (multiple of 8) */
+  int a_mn, b_mn;
+  int epi, act;
+  void* out;
+  int ldo;       /* multiple of 8 */
+  int out_fp32;  /* 1: float output, 0: bf16 output */
+  const float* bias; /* [N] or NULL */
+  void* aux;     /* bf16 [M, ld_aux], see epilogue kinds */
+  int ld_aux;
+  const float* resid; /* fp32 [M, ld_resid] or NULL */
+  int ld_resid;
+  const float* gate;  /* fp32 [M / rows_per_group, ld_gate] */
+  int ld_gate;
+  int rows_per_group;
+  int block_n;   /* 0 = auto, or 128/192/256 */
+} mdt_gemm_args;
+
+int mdt_gemm_bf16(const mdt_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Mask index path (integer, bit-exact).  get_mask, models/maskdit.py:88-113: ids_shuffle = argsort(noise),
+ * ids_restore = argsort(ids_shuffle), ids_keep = ids_shuffle[:, :len_keep], mask = (ids_restore >= len_keep).
+ * Ties in `noise` are broken by ascending index (= torch.argsort(stable=True)).
+ *   noise [B,L] f32 -> ids_keep [B,len_keep] i64, ids_restore [B,L] i64, mask [B,L] f32 (0 keep / 1 remove)
+ * ------------------------------------------------------------------------------------------------------------ */
+int mdt_mask_indices(const float* noise, int B, int L, int len_keep, int64_t* ids_keep, int64_t* ids_restore,
+                     float* mask, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * PatchEmbed + pos_embed + mask_out_token + EDM c_in scaling, fused.
+ * models/maskdit.py:475 (x_embedder(x) + pos_embed), :126 (gather kept tokens), :764-769 (c_in * x).
+ *   x [B,C,R,R] f32, sigma [B] f32 or NULL (c_in = 1/sqrt(sigma_data^2+sigma^2), 1 if NULL),
+ *   W [D, C*p*p] f32 (Conv2d weight flattened (c,ph,pw)), bias [D], pos [L,D] f32,
+ *   ids_keep [B,T] i64 or NULL (NULL: T == L, identity) -> out [B,T,D] f32
+ * Backward: gW [D, C*p*p] += sum g (x) patch, gb [D] += sum g    (no input gradient is needed)
+ * ------------------------------------------------------------------------------------------------------------ */
+int mdt_patch_embed(const float* x, const float* sigma, float sigma_data, const float* W, const float* bias,
+                    const float* pos, const int64_t* ids_keep, float* out, int B, int C, int R, int p, int D, int T,
+                    void* stream);
+int mdt_patch_embed_bwd(const float* x, const float* sigma, float sigma_data, const int64_t* ids_keep,
+                        const float* g, float* gW, float* gb, int B, int C, int R, int p, int D, int T, void* stream);
+
+/* TimestepEmbedder.timestep_embedding (models/maskdit.py:41-58) on t = c_noise = ln(sigma)/4 (:767):
+ *   out[b] = [cos(t f_k) | sin(t f_k)], f_k = exp(-ln(1e4) k / (dim/2)); out bf16 [B, dim]                  */
+int mdt_timestep_freq(const float* sigma, int B, int dim, void* out_bf16, void* stream);
+
+/* Pointwise helpers around the conditioning MLPs (nn.SiLU at models/maskdit.py:36,184,205,226).
+ *   silu:      out_bf16 = silu(a [+ b])  (and out_f32 = a + b if non-NULL)
+ *   silu_bwd:  dx = dy * silu'(x)                                                                            */
+int mdt_silu(const float* a, const float* b, float* sum_f32, void* out_bf16, long long n, void* stream);
+int mdt_silu_bwd(const float* dy, const float* x, float* dx_f32, void* dx_bf16, long long n, void* stream);
+int mdt_cast_f32_bf16(const float* in, void* out_bf16, long long n, void* stream);
+/* column sums: out[N] (+)= sum_m in[m, n]  (bias gradients) */
+int mdt_colsum_bf16(const void* in_bf16, int M, int N, int ld, float* out, void* stream);
+int mdt_colsum_f32(const float* in, int M, int N, int ld, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * LayerNorm(no affine, eps) + modulate, models/maskdit.py:19-20,177,179,190-191,202,211,223,232:
+ *   out_bf16[m,:] = LN(x[m,:]) * (1 + scale[m / rows_per_group,:]) + shift[m / rows_per_group,:]
+ * saves mean/rstd [M] for the backward.  shift/scale are fp32 with row stride ld_mod.
+ * Backward (dxmod bf16 -> residual-stream gradient, fp32):
+ *   g[m,:] (+)= d LN / dx ; dshift[b,:] += sum_t dxmod ; dscale[b,:] += sum_t dxmod * xhat
+ * ------------------------------------------------------------------------------------------------------------ */
+int mdt_ln_modulate(const float* x, const float* shift, const float* scale, int ld_mod, int rows_per_group,
+                    void* out_bf16, float* mean, float* rstd, int M, int D, float eps, void* stream);
+int mdt_ln_modulate_bwd(const void* dxmod_bf16, const float* x, const float* mean, const float* rstd,
+                        const float* scale, int ld_mod, int rows_per_group, float* g, int accumulate,
+                        float* dshift, float* dscale, int ld_dmod, int M, int D, void* stream);
+
+/* Backward of  x_out = x + gate * y  (models/maskdit.py:190-191) w.r.t. y and gate, plus the bias gradient of the
+ * Linear that produced y:  dy_bf16 = g * gate ; dgate[b,:] += sum_t g*y ; dbias[:] += sum_m dy                 */
+int mdt_gate_bwd(const float* g, const void* y_bf16, const float* gate, int ld_gate, int rows_per_group,
+                 void* dy_bf16, float* dgate, int ld_dgate, float* dbias, int M, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-head attention core of timm Attention (ctor models/maskdit.py:178):
+ *   qkv [B,T,3,H,dh] bf16 -> out [B,T,H*dh] bf16 = softmax(q k^T / sqrt(dh)) v ; lse [B,H,T] f32 (log-sum-exp)
+ * Backward: dqkv [B,T,3,H,dh] bf16 from dout.
+ * ------------------------------------------------------------------------------------------------------------ */
+int mdt_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, void* stream);
+int mdt_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int T,
+                      int H, int dh, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * unmask_tokens + decoder_pos_embed (models/maskdit.py:157-163,543-545):
+ *   out[b,l,:] = (ids_restore[b,l] < T ? u[b, ids_restore[b,l], :] : mask_token) + pos[l,:]
+ * ids_restore NULL = eval path (no masking): out = u + pos.
+ * Backward: du_bf16[b,i,:] = g[b, ids_keep[b,i], :] ; dmask_token[:] += sum over removed positions of g.
+ * ------------------------------------------------------------------------------------------------------------ */
+int mdt_unmask_tokens(const float* u, const float* mask_token, const float* pos, const int64_t* ids_restore,
+                      float* out, int B, int T, int L, int D, void* stream);
+int mdt_unmask_tokens_bwd(const float* g, const int64_t* ids_keep, const int64_t* ids_restore, void* du_bf16,
+                          float* dmask_token, int B, int T, int L, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * unpatchify + EDM preconditioning + EDM/MAE loss, forward and the gradient seed in one pass.
+ *   F [B,L,p*p*C] f32 (final_layer output) ; xin [B,C,R,R] noisy input y+n ; y [B,C,R,R] clean ; sigma [B]
+ *   D = c_skip*xin + c_out*unpatchify(F)                    models/maskdit.py:411-424,764-771
+ *   mask != NULL: loss[b] = mean_{kept}(patch-mean(w (D-y)^2)) + mae_coef * mean_{removed}(MSE(patchify(D), norm-patchify(xin)))
+ *                                                            train_utils/loss.py:37,44-52,73-101
+ *   mask == NULL: loss[b] = mean(w (D-y)^2)                  loss.py:54
+ *   dF_bf16 (optional) = d(sum_b gl[b]*loss[b]) / dF ; Dx (optional) [B,C,R,R] f32.
+ * ------------------------------------------------------------------------------------------------------------ */
+int mdt_edm_loss(const float* F, const float* xin, const float* y, const float* sigma, const float* mask,
+                 const float* gl, float sigma_data, float mae_coef, float* loss, float* Dx, void* dF_bf16, int B,
+                 int C, int R, int p, void* stream);
+/* D only (sampler / generic autograd path): Dx = c_skip*xin + c_out*unpatchify(F); and its backward
+ * dF_bf16 = c_out * patchify(gD).                                                                            */
+int mdt_edm_precond_out(const float* F, const float* xin, const float* sigma, float sigma_data, float* Dx, int B,
+                        int C, int R, int p, void* stream);
+int mdt_edm_precond_out_bwd(const float* gD, const float* sigma, float sigma_data, void* dF_bf16, int B, int C, int R,
+                            int p, void* stream);
+
+/* Classifier-free guidance combine (forward_with_cfg, models/maskdit.py:580-583) fused with the EDM output scaling:
+ *   F [2B,L,p*p*C] (cond rows first, uncond rows second) -> Dx [B,C,R,R] = c_skip*x + c_out*(Fu + s (Fc - Fu))  */
+int mdt_cfg_precond_out(const float* F, const float* xin, const float* sigma, float sigma_data, float cfg_scale,
+                        float* Dx, int B, int C, int R, int p, void* stream);
+
+/* EDM Heun sampler state update in fp64 (sample.py:56-64):
+ *   mode 0 (Euler):  d_cur = (x_hat - den)/t_hat ; x_next = x_hat + (t_next - t_hat) d_cur
+ *   mode 1 (Heun):   d_prime = (x_next - den)/t_next ; x_next = x_hat + (t_next - t_hat)(0.5 d_cur + 0.5 d_prime) */
+int mdt_heun_update(int mode, const double* x_hat, const float* denoised, double* d_cur, double* x_next,
+                    float* x_next_f32, double t_hat, double t_next, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused AdamW (weight_decay handled as adam_w_mode, train.py:141) + EMA (train_utils/helper.py:47-58) + bf16
+ * weight-shadow refresh over flat buffers:  one pass instead of apex multi_tensor_adam + a 376-launch EMA loop.
+ *   g is multiplied by grad_scale first (1/world_size after a SUM all-reduce).  ema / w_bf16 may be NULL.
+ * ------------------------------------------------------------------------------------------------------------ */
+int mdt_adamw_ema(float* w, const float* g, float* m, float* v, float* ema, void* w_bf16, long long n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, float ema_decay,
+                  float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MASKDIT_B200_H_ */

@@ -1,0 +1,140 @@
+"""ctypes binding of `libmaskdit_b200.so` (the C ABI declared in include/maskdit_b200.h).
+
+There is NO fallback: if the CUDA library is missing or a kernel returns a non-zero status this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmaskdit_b200.so")
+
+
+class MdtError(RuntimeError):
+    pass
+
+
+class GemmArgs(Structure):
+    _fields_ = [
+        ("A", c_void_p), ("B", c_void_p),
+        ("M", c_int), ("N", c_int), ("K", c_int),
+        ("lda", c_int), ("ldb", c_int),
+        ("a_mn", c_int), ("b_mn", c_int),
+        ("epi", c_int), ("act", c_int),
+        ("out", c_void_p), ("ldo", c_int), ("out_fp32", c_int),
+        ("bias", c_void_p),
+        ("aux", c_void_p), ("ld_aux", c_int),
+        ("resid", c_void_p), ("ld_resid", c_int),
+        ("gate", c_void_p), ("ld_gate", c_int),
+        ("rows_per_group", c_int),
+        ("block_n", c_int),
+    ]
+
+
+EPI_STORE, EPI_GELU, EPI_GATE_RESID, EPI_DGELU, EPI_ATOMIC = range(5)
+ACT_NONE, ACT_SILU = 0, 1
+
+_lib = None
+
+# name -> argtypes  (every function returns int status; last arg is the stream)
+_P, _I, _F, _LL, _D = c_void_p, c_int, c_float, c_longlong, c_double
+_SIGS = {
+    "mdt_gemm_bf16": [POINTER(GemmArgs), _P],
+    "mdt_mask_indices": [_P, _I, _I, _I, _P, _P, _P, _P],
+    "mdt_patch_embed": [_P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mdt_patch_embed_bwd": [_P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mdt_timestep_freq": [_P, _I, _I, _P, _P],
+    "mdt_silu": [_P, _P, _P, _P, _LL, _P],
+    "mdt_silu_bwd": [_P, _P, _P, _P, _LL, _P],
+    "mdt_cast_f32_bf16": [_P, _P, _LL, _P],
+    "mdt_colsum_bf16": [_P, _I, _I, _I, _P, _P],
+    "mdt_colsum_f32": [_P, _I, _I, _I, _P, _P],
+    "mdt_ln_modulate": [_P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _F, _P],
+    "mdt_ln_modulate_bwd": [_P, _P, _P, _P, _P, _I, _I, _P, _I, _P, _P, _I, _I, _I, _P],
+    "mdt_gate_bwd": [_P, _P, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P],
+    "mdt_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "mdt_attention_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mdt_unmask_tokens": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mdt_unmask_tokens_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mdt_edm_loss": [_P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mdt_edm_precond_out": [_P, _P, _P, _F, _P, _I, _I, _I, _I, _P],
+    "mdt_edm_precond_out_bwd": [_P, _P, _F, _P, _I, _I, _I, _I, _P],
+    "mdt_cfg_precond_out": [_P, _P, _P, _F, _F, _P, _I, _I, _I, _I, _P],
+    "mdt_heun_update": [_I, _P, _P, _P, _P, _P, _D, _D, _LL, _P],
+    "mdt_adamw_ema": [_P, _P, _P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _F, _P],
+}
+
+
+def lib():
+    """Load the CUDA library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MdtError(
+                f"{LIB_PATH} not found: build it with `python -m maskdit_b200.build` "
+                "(there is no CPU / PyTorch fallback for the MaskDiT hot path)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.mdt_status_string.restype = c_char_p
+        L.mdt_status_string.argtypes = [c_int]
+        L.mdt_abi_version.restype = c_int
+        for name, sig in _SIGS.items():
+            if not hasattr(L, name) and os.environ.get("MDT_ALLOW_PARTIAL_LIB") == "1":
+                continue  # development only: probing a partially built library
+            fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol -> loud
+            fn.restype = c_int
+            fn.argtypes = sig
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return ["mdt_status_string", "mdt_abi_version", *_SIGS.keys()]
+
+
+def check(status: int, what: str):
+    if status != 0:
+        msg = lib().mdt_status_string(status).decode()
+        raise MdtError(f"{what} failed: {msg} (status {status})")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise MdtError("maskdit_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+def gemm(A, B, M, N, K, *, lda=None, ldb=None, a_mn=False, b_mn=False, epi=EPI_STORE, act=ACT_NONE, out=None,
+         ldo=None, bias=None, aux=None, ld_aux=0, resid=None, ld_resid=0, gate=None, ld_gate=0, rows_per_group=1,
+         block_n=0):
+    """out[M,N] (+)= sum_k A[m,k] B[n,k].  `out` dtype (bf16/fp32) selects the store type."""
+    _req_cuda(A, B, out)
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    assert out is not None and out.dtype in (torch.bfloat16, torch.float32)
+    a = GemmArgs()
+    a.A, a.B = A.data_ptr(), B.data_ptr()
+    a.M, a.N, a.K = M, N, K
+    a.lda = lda if lda is not None else (M if a_mn else K)
+    a.ldb = ldb if ldb is not None else (N if b_mn else K)
+    a.a_mn, a.b_mn = int(a_mn), int(b_mn)
+    a.epi, a.act = epi, act
+    a.out, a.ldo, a.out_fp32 = out.data_ptr(), (ldo if ldo is not None else N), int(out.dtype == torch.float32)
+    a.bias = ptr(bias)
+    a.aux, a.ld_aux = ptr(aux), ld_aux
+    a.resid, a.ld_resid = ptr(resid), ld_resid
+    a.gate, a.ld_gate = ptr(gate), ld_gate
+    a.rows_per_group = rows_per_group
+    a.block_n = block_n
+    check(lib().mdt_gemm_bf16(ctypes.byref(a), stream_ptr()), "mdt_gemm_bf16")
+    return out

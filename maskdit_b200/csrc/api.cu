@@ -1,0 +1,25 @@
+// extern "C" surface that is not tied to one kernel file: status strings, ABI version, GEMM entry.
+#include "gemm.h"
+
+extern "C" {
+
+const char* mdt_status_string(int status) {
+  switch (status) {
+    case MDT_OK: return "ok";
+    case MDT_ERR_ARG: return "invalid argument (shape / alignment / null pointer)";
+    case MDT_ERR_CUDA: return "CUDA launch failure";
+    case MDT_ERR_DRIVER: return "cuTensorMapEncodeTiled driver entry point unavailable";
+    case MDT_ERR_TMAP: return "tensor map encode failed";
+    case MDT_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown status";
+  }
+}
+
+int mdt_abi_version(void) { return 1; }
+
+int mdt_gemm_bf16(const mdt_gemm_args* args, void* stream) {
+  if (!args || !args->A || !args->B || !args->out) return MDT_ERR_ARG;
+  return mdt::gemm_launch(*args, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

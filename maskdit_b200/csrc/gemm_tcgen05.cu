@@ -1,0 +1,473 @@
+// bf16 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+//
+//   out[M,N] (+)= sum_k A[m,k] * B[n,k]      fp32 accumulate
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer   (one thread)  global -> 128B-swizzled smem ring, mbarrier complete_tx
+//   warp 1      MMA issuer     (one thread)  tcgen05.mma 128 x BLOCK_N x 16, tcgen05.commit -> barriers
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue       tcgen05.ld (lane group = warp % 4, column half = (warp-4)/4) -> fused epilogue
+// Two TMEM accumulator stages so the epilogue of unit i overlaps the MMAs of unit i+1.
+//
+// Operand majors: "K-major" = contraction index contiguous in memory (activations [M,K], nn.Linear weights
+// [N,K]); "MN-major" = the M/N index contiguous (used by dgrad: B = W[N,K] read as [K_out, N_contract]; and by
+// wgrad: both operands are token-major [tokens, features] with the contraction over tokens).
+//
+// Scheduling: tile mode (each CTA takes whole output tiles, strided) for forward/dgrad, and stream-K mode
+// (the (tile, k-block) iteration space is cut into equal contiguous ranges, partial tiles reduced with fp32
+// red.global.add) for wgrad / small-output GEMMs whose tile count does not fill 148 SMs.
+//
+// Reference ops this replaces: every nn.Linear of models/maskdit.py (timm Attention.qkv/proj, Mlp.fc1/fc2,
+// adaLN_modulation, DecoderLayer.linear, TimestepEmbedder.mlp, LabelEmbedder) and their autograd backward.
+#include "common.cuh"
+#include "gemm.h"
+
+#include <mutex>
+#include <unordered_map>
+
+namespace mdt {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int kNumEpiWarps = 8;
+constexpr int kNumThreads = 128 + kNumEpiWarps * 32;  // 384
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192 ? 5 : 6);
+  static constexpr int kTmemCols = (2 * BLOCK_N > 256) ? 512 : 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct UnitSched {
+  // Iterates the work units of this CTA; identical sequence in every warp role.
+  int mode, num_kb, num_tiles, num_n_tiles;
+  long long it, it_end;  // stream-K: global iteration range
+  int tile, grid;        // tile mode
+  int cur_tile, kb0, kb1;
+  MDT_DEVINL void init(const GemmParams& p) {
+    mode = p.streamk;
+    num_kb = p.num_kb;
+    num_n_tiles = p.num_n_tiles;
+    num_tiles = p.num_m_tiles * p.num_n_tiles;
+    grid = gridDim.x;
+    if (mode) {
+      long long total = static_cast<long long>(num_tiles) * num_kb;
+      it = total * blockIdx.x / grid;
+      it_end = total * (blockIdx.x + 1) / grid;
+    } else {
+      tile = blockIdx.x;
+    }
+  }
+  MDT_DEVINL bool next() {
+    if (mode) {
+      if (it >= it_end) return false;
+      cur_tile = static_cast<int>(it / num_kb);
+      kb0 = static_cast<int>(it % num_kb);
+      long long rem = it_end - it;
+      kb1 = (num_kb - kb0 < rem) ? num_kb : kb0 + static_cast<int>(rem);
+      it += kb1 - kb0;
+      return true;
+    } else {
+      if (tile >= num_tiles) return false;
+      cur_tile = tile;
+      kb0 = 0;
+      kb1 = num_kb;
+      tile += grid;
+      return true;
+    }
+  }
+  MDT_DEVINL int m_tile() const { return cur_tile / num_n_tiles; }
+  MDT_DEVINL int n_tile() const { return cur_tile % num_n_tiles; }
+};
+
+// ---- fused epilogue on a 32-column chunk held by one thread (one output row) -------------------------------
+MDT_DEVINL void store_bf16x32(__nv_bfloat16* dst, const float* v, int ncols) {
+  if (ncols == 32) {
+    uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 q;
+      q.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+      q.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+      q.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+      q.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+      d[i] = q;
+    }
+  } else {
+    for (int i = 0; i < ncols; ++i) dst[i] = __float2bfloat16_rn(v[i]);
+  }
+}
+MDT_DEVINL void store_f32x32(float* dst, const float* v, int ncols) {
+  if (ncols == 32) {
+    float4* d = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    for (int i = 0; i < ncols; ++i) dst[i] = v[i];
+  }
+}
+MDT_DEVINL void load_f32x32(const float* src, float* v, int ncols) {
+  if (ncols == 32) {
+    const float4* s = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 q = s[i];
+      v[4 * i] = q.x, v[4 * i + 1] = q.y, v[4 * i + 2] = q.z, v[4 * i + 3] = q.w;
+    }
+  } else {
+    for (int i = 0; i < 32; ++i) v[i] = (i < ncols) ? src[i] : 0.f;
+  }
+}
+MDT_DEVINL void load_bf16x32(const __nv_bfloat16* src, float* v, int ncols) {
+  if (ncols == 32) {
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 q = s[i];
+      v[8 * i + 0] = bf16_lo(q.x), v[8 * i + 1] = bf16_hi(q.x);
+      v[8 * i + 2] = bf16_lo(q.y), v[8 * i + 3] = bf16_hi(q.y);
+      v[8 * i + 4] = bf16_lo(q.z), v[8 * i + 5] = bf16_hi(q.z);
+      v[8 * i + 6] = bf16_lo(q.w), v[8 * i + 7] = bf16_hi(q.w);
+    }
+  } else {
+    for (int i = 0; i < 32; ++i) v[i] = (i < ncols) ? __bfloat162float(src[i]) : 0.f;
+  }
+}
+
+MDT_DEVINL void epilogue_chunk(const GemmParams& p, int row, int col0, int ncols, float* acc, bool partial) {
+  const size_t o = static_cast<size_t>(row) * p.ldo + col0;
+  if (p.epi == EPI_ATOMIC || partial) {
+    float* out = reinterpret_cast<float*>(p.out) + o;
+    for (int i = 0; i < ncols; ++i) atomicAdd(out + i, acc[i]);
+    return;
+  }
+  if (p.bias) {
+    float b[32];
+    load_f32x32(p.bias + col0, b, ncols);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] += b[i];
+  }
+  switch (p.epi) {
+    case EPI_STORE: {
+      if (p.act == ACT_SILU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = silu(acc[i]);
+      }
+      if (p.out_fp32)
+        store_f32x32(reinterpret_cast<float*>(p.out) + o, acc, ncols);
+      else
+        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out) + o, acc, ncols);
+    } break;
+    case EPI_GELU: {
+      // pre-activation is rounded to bf16 first (as a bf16 nn.Linear output would be), GELU on the rounded value
+      __nv_bfloat16* pre = reinterpret_cast<__nv_bfloat16*>(p.aux) + static_cast<size_t>(row) * p.ld_aux + col0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = round_bf16(acc[i]);
+      if (p.aux) store_bf16x32(pre, acc, ncols);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = gelu_tanh(acc[i]);
+      store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out) + o, acc, ncols);
+    } break;
+    case EPI_GATE_RESID: {
+      if (p.aux)
+        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.aux) + static_cast<size_t>(row) * p.ld_aux + col0, acc,
+                      ncols);
+      float g[32], r[32];
+      load_f32x32(p.gate + static_cast<size_t>(row / p.rows_per_group) * p.ld_gate + col0, g, ncols);
+      load_f32x32(p.resid + static_cast<size_t>(row) * p.ld_resid + col0, r, ncols);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = fmaf(g[i], acc[i], r[i]);
+      store_f32x32(reinterpret_cast<float*>(p.out) + o, acc, ncols);
+    } break;
+    case EPI_DGELU: {
+      float h[32];
+      load_bf16x32(reinterpret_cast<const __nv_bfloat16*>(p.aux) + static_cast<size_t>(row) * p.ld_aux + col0, h,
+                   ncols);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] *= gelu_tanh_grad(h[i]);
+      store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out) + o, acc, ncols);
+    } break;
+    default: break;
+  }
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_tiles = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;           // [kStages]  MMA -> TMA
+  uint64_t* tmem_full_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]        epilogue -> MMA
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], kNumEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_base_smem);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  UnitSched sched;
+  sched.init(p);
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    while (sched.next()) {
+      const int m0 = sched.m_tile() * BLOCK_M, n0 = sched.n_tile() * BLOCK_N;
+      for (int kb = sched.kb0; kb < sched.kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem_tiles + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        const int k0 = kb * BLOCK_K;
+        if constexpr (!A_MN) {
+          tma_load_2d(&tmap_a, &full_bar[stage], sa, k0, m0);  // box {64 k, 128 rows}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BLOCK_M / 64; ++j)  // boxes {64 mn, 64 k}
+            tma_load_2d(&tmap_a, &full_bar[stage], sa + j * (64 * BLOCK_K * 2), m0 + j * 64, k0);
+        }
+        if constexpr (!B_MN) {
+          tma_load_2d(&tmap_b, &full_bar[stage], sb, k0, n0);  // box {64 k, BLOCK_N rows}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_2d(&tmap_b, &full_bar[stage], sb + j * (64 * BLOCK_K * 2), n0 + j * 64, k0);
+        }
+        if (++stage == kStages) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    while (sched.next()) {
+      mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+      for (int kb = sched.kb0; kb < sched.kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem_tiles + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // K-major: +32 B per UMMA_K inside the 128B swizzle row; SBO = 8 rows * 128 B.
+          // MN-major: +16 k-rows * 128 B per UMMA_K; LBO = one 64-wide MN atom (64 k-rows * 128 B), SBO = 8 k-rows.
+          const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * (UMMA_K * 128), 64 * BLOCK_K * 2, 1024)
+                                   : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
+          const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), 64 * BLOCK_K * 2, 1024)
+                                   : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
+          umma_bf16(tmem_d, da, db, idesc, (kb > sched.kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+        if (++stage == kStages) stage = 0, phase ^= 1;
+      }
+      umma_commit(&tmem_full_bar[as]);  // accumulator complete -> epilogue
+      if (++as == 2) as = 0, aphase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;
+    const int lane_group = warp & 3;           // tcgen05.ld: warp w may touch TMEM lanes 32*(w%4)..+31
+    const int col_half = ew >> 2;              // 0/1
+    constexpr int kColsPerWarp = BLOCK_N / 2;  // 128 / 96 / 64
+    int as = 0;
+    uint32_t aphase = 0;
+    while (sched.next()) {
+      const int m0 = sched.m_tile() * BLOCK_M, n0 = sched.n_tile() * BLOCK_N;
+      const bool partial = p.streamk && !(sched.kb0 == 0 && sched.kb1 == p.num_kb && p.epi != EPI_ATOMIC);
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tcgen05_fence_after();
+      const int row = m0 + lane_group * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * BLOCK_N +
+                             col_half * kColsPerWarp;
+#pragma unroll 1
+      for (int c = 0; c < kColsPerWarp; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c, r);
+        tcgen05_wait_ld();
+        const int col0 = n0 + col_half * kColsPerWarp + c;
+        int ncols = p.N - col0;
+        ncols = ncols > 32 ? 32 : ncols;
+        if (row < p.M && ncols > 0) {
+          float acc[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(r[i]);
+          epilogue_chunk(p, row, col0, ncols, acc, partial);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (++as == 2) as = 0, aphase ^= 1;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map: dims {inner, outer}, row stride ld elements, box {box_inner, box_outer}, 128B swizzle.
+static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                     uint32_t box_outer) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return MDT_ERR_DRIVER;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MDT_OK : MDT_ERR_TMAP;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = kNumSMsDefault;
+  }
+  return g_num_sms;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  CUtensorMap ta, tb;
+  int rc;
+  // A: K-major stored [M, K] ld=lda -> dims {K, M}, box {64, 128}; MN-major stored [K, M] -> dims {M, K}, box {64, 64}
+  rc = A_MN ? make_tmap(&ta, a.A, a.M, a.K, a.lda, 64, 64) : make_tmap(&ta, a.A, a.K, a.M, a.lda, 64, BLOCK_M);
+  if (rc) return rc;
+  rc = B_MN ? make_tmap(&tb, a.B, a.N, a.K, a.ldb, 64, 64) : make_tmap(&tb, a.B, a.K, a.N, a.ldb, 64, BLOCK_N);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.M = a.M, p.N = a.N, p.K = a.K;
+  p.epi = a.epi, p.act = a.act;
+  p.num_m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
+  p.num_kb = (a.K + BLOCK_K - 1) / BLOCK_K;
+  p.out = a.out, p.ldo = a.ldo, p.out_fp32 = a.out_fp32;
+  p.bias = a.bias;
+  p.aux = a.aux, p.ld_aux = a.ld_aux;
+  p.resid = a.resid, p.ld_resid = a.ld_resid;
+  p.gate = a.gate, p.ld_gate = a.ld_gate, p.rows_per_group = a.rows_per_group > 0 ? a.rows_per_group : 1;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int sms = num_sms();
+  // stream-K whenever the epilogue is a pure fp32 accumulation
+  p.streamk = (a.epi == EPI_ATOMIC) ? 1 : 0;
+  int grid;
+  if (p.streamk) {
+    long long total = static_cast<long long>(tiles) * p.num_kb;
+    grid = total < sms ? static_cast<int>(total) : sms;
+  } else {
+    grid = tiles < sms ? tiles : sms;
+  }
+  if (grid <= 0) return MDT_OK;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return MDT_ERR_CUDA;
+    attr_set = true;
+  }
+  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  return cudaGetLastError() == cudaSuccess ? MDT_OK : MDT_ERR_CUDA;
+}
+
+template <bool A_MN, bool B_MN>
+static int dispatch_n(const mdt_gemm_args& a, cudaStream_t stream) {
+  // pick the tile width that wastes the fewest columns; ties -> wider tile
+  int best = 256;
+  long long best_cost = -1;
+  const int cands[3] = {256, 192, 128};
+  for (int c : cands) {
+    long long cost = static_cast<long long>((a.N + c - 1) / c) * c;
+    if (best_cost < 0 || cost < best_cost) best = c, best_cost = cost;
+  }
+  if (a.block_n == 128 || a.block_n == 192 || a.block_n == 256) best = a.block_n;
+  switch (best) {
+    case 256: return launch<256, A_MN, B_MN>(a, stream);
+    case 192: return launch<192, A_MN, B_MN>(a, stream);
+    default: return launch<128, A_MN, B_MN>(a, stream);
+  }
+}
+
+int gemm_launch(const mdt_gemm_args& a, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return MDT_ERR_ARG;
+  if ((a.lda % 8) || (a.ldb % 8)) return MDT_ERR_ARG;                                   // TMA: 16-byte row strides
+  if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.B) & 15)) return MDT_ERR_ARG;
+  if (a.epi == EPI_ATOMIC && !a.out_fp32) return MDT_ERR_ARG;
+  if (a.epi == EPI_GATE_RESID && (!a.gate || !a.resid)) return MDT_ERR_ARG;
+  if (a.epi == EPI_DGELU && !a.aux) return MDT_ERR_ARG;
+  // vectorised epilogue accesses need 32-column chunks to start 16B-aligned
+  if (a.ldo % 8) return MDT_ERR_ARG;
+  if (a.a_mn && a.b_mn) return dispatch_n<true, true>(a, stream);
+  if (!a.a_mn && a.b_mn) return dispatch_n<false, true>(a, stream);
+  if (!a.a_mn && !a.b_mn) return dispatch_n<false, false>(a, stream);
+  return MDT_ERR_ARG;  // (MN, K) is never needed by this path
+}
+
+}  // namespace mdt

@@ -154,6 +154,12 @@ MDT_DEVINL void epilogue_chunk(const GemmParams& p, int row, int col0, int ncols
   }
   switch (p.epi) {
     case EPI_STORE: {
+      if (p.resid) {
+        float r[32];
+        load_f32x32(p.resid + static_cast<size_t>(row) * p.ld_resid + col0, r, ncols);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] += r[i];
+      }
       if (p.act == ACT_SILU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = silu(acc[i]);
@@ -310,7 +316,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t aphase = 0;
     while (sched.next()) {
       const int m0 = sched.m_tile() * BLOCK_M, n0 = sched.n_tile() * BLOCK_N;
-      const bool partial = p.streamk && !(sched.kb0 == 0 && sched.kb1 == p.num_kb && p.epi != EPI_ATOMIC);
+      const bool partial = p.streamk != 0;
       mbar_wait(&tmem_full_bar[as], aphase);
       tcgen05_fence_after();
       const int row = m0 + lane_group * 32 + lane;

@@ -1,0 +1,101 @@
+"""Data-parallel training step on the B200 engine (reference: train.py:200-230 inner step, :178 DDP, :141 optimizer,
+train_utils/helper.py:47-58 EMA).
+
+One process per GPU.  A step is:
+    zero flat grad  ->  fused EDM loss forward/backward (engine)  ->  ONE NCCL all-reduce of the flat fp32 gradient
+    buffer over NVLink (SUM; the 1/world factor is folded into the optimizer kernel)  ->  ONE fused
+    AdamW + EMA + bf16-shadow kernel over the flat buffers.
+No other collective is issued in the step; the loss is returned as a device tensor (no per-step
+`.item()` host sync as at train.py:227).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .loss import EDMLoss
+from .maskdit import EDMPrecond
+
+
+class DataParallelB200:
+    """What the reference's loss expects from the DDP wrapper: `.module`, `.training`, callable (loss.py:41,47,52).
+    Gradient synchronisation is NOT hooked into autograd; `TrainStep` all-reduces the flat gradient buffer once."""
+
+    def __init__(self, module: EDMPrecond):
+        self.module = module
+
+    @property
+    def training(self):
+        return self.module.training
+
+    def train(self, mode=True):
+        self.module.train(mode)
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def parameters(self):
+        return self.module.parameters()
+
+    def __call__(self, *a, **k):
+        return self.module(*a, **k)
+
+
+def shard_batch(global_batch: int, world_size: int, rank: int):
+    """Even batch split by rank (train.py:72-75: global = per-GPU batch x world)."""
+    if global_batch % world_size:
+        raise ValueError(f"global batch {global_batch} not divisible by world size {world_size}")
+    per = global_batch // world_size
+    return rank * per, (rank + 1) * per
+
+
+def lr_at(step: int, base_lr: float, global_batch: int, rampup_kimg: float):
+    """train.py:223 — note lr = 0 at step 0 when rampup_kimg > 0; with rampup 0 it is base_lr from step 1 on."""
+    return base_lr * min(step * global_batch / max(rampup_kimg * 1000, 1e-8), 1)
+
+
+class TrainStep:
+    def __init__(self, net: EDMPrecond, ema: EDMPrecond | None = None, lr=1e-4, betas=(0.9, 0.999), eps=1e-8,
+                 weight_decay=0.0, ema_decay=0.9999, loss_fn: EDMLoss | None = None, process_group=None,
+                 lr_rampup_kimg=0.0, global_batch=None, device=None):
+        self.net, self.ema = net, ema
+        self.lr, self.betas, self.eps, self.wd, self.ema_decay = lr, betas, eps, weight_decay, ema_decay
+        self.loss_fn = loss_fn or EDMLoss()
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.rampup, self.global_batch = lr_rampup_kimg, global_batch
+        self.step_count = 0
+        dev = device or next(net.parameters()).device
+        self.st = net.prepare(dev)
+        self.st.ensure_grad()
+        n = self.st.n_train
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.ema_st = None
+        if ema is not None:
+            self.ema_st = ema.prepare(dev)
+            assert self.ema_st.n_train == n and self.ema_st.offsets == self.st.offsets
+        for k, p in net.named_parameters():  # .grad views into the flat buffer (optimizer-compatible)
+            if p.requires_grad:
+                p.grad = self.st.gview(k)
+
+    def step(self, images, labels, mask_ratio=0.5, mae_loss_coef=0.1):
+        """One optimisation step on this rank's shard.  Returns the per-sample loss [B] (device tensor)."""
+        st = self.st
+        st.grad.zero_()
+        loss = self.loss_fn(self.net, images, labels, mask_ratio=mask_ratio, mae_loss_coef=mae_loss_coef)
+        loss.mean().backward()
+        if self.world > 1:
+            dist.all_reduce(st.grad, op=dist.ReduceOp.SUM, group=self.pg)  # the step's only collective
+        self.step_count += 1
+        gb = self.global_batch or images.shape[0] * self.world
+        lr = lr_at(self.step_count, self.lr, gb, self.rampup) if self.rampup > 0 else self.lr
+        ops.adamw_ema(st.w32, st.grad, self.m, self.v, self.ema_st.w32 if self.ema_st is not None else None, st.w16,
+                      st.n_train, lr, self.step_count, self.betas[0], self.betas[1], self.eps, self.wd,
+                      self.ema_decay, 1.0 / self.world)
+        st.mark_shadow_fresh(self.net._params())   # the kernel refreshed the bf16 shadow itself
+        if self.ema_st is not None:
+            self.ema_st._versions = None           # EMA weights changed behind PyTorch's back: shadow is stale
+        return loss.detach()

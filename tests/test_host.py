@@ -1,0 +1,139 @@
+"""CPU tests of the host-side logic: ABI surface, module/state-dict contract, flat layout, DP helpers (gloo)."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads without a GPU and exports every function include/maskdit_b200.h declares."""
+    from maskdit_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "maskdit_b200.h")).read()
+    declared = set(re.findall(r"\b(mdt_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("mdt_gemm_args")
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
+    assert _lib.lib().mdt_abi_version() == 1
+    assert _lib.lib().mdt_status_string(-1).decode().startswith("invalid argument")
+
+
+def test_product_path_refuses_cpu_tensors():
+    from maskdit_b200 import ops
+    from maskdit_b200._lib import MdtError
+    from maskdit_b200.maskdit import Precond_models
+    with pytest.raises(MdtError):
+        ops.mask_indices(torch.rand(2, 16), 8)
+    net = Precond_models["edm"](8, 4, num_classes=10, model_type="DiT-S/2", use_decoder=True, mae_loss_coef=0.1)
+    with pytest.raises(MdtError):
+        net(torch.randn(2, 4, 8, 8), torch.ones(2), None)
+
+
+def test_product_never_imports_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "maskdit_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), f
+
+
+@pytest.mark.parametrize("mt,R,ncls", [("DiT-S/2", 8, 10), ("DiT-XL/2", 32, 1000)])
+def test_state_dict_contract_matches_reference_keys(mt, R, ncls):
+    """Key names and shapes of EDMPrecond.state_dict() == the reference's (oracle.param_shapes is pinned to the
+    reference module by make_golden.py's strict load)."""
+    from maskdit_b200.maskdit import DiT_models, Precond_models
+    from oracle import maskdit_oracle as O
+    if mt == "DiT-XL/2":
+        with torch.device("meta"):
+            net = Precond_models["edm"](R, 4, num_classes=ncls, model_type=mt, use_decoder=True, mae_loss_coef=0.1)
+    else:
+        net = Precond_models["edm"](R, 4, num_classes=ncls, model_type=mt, use_decoder=True, mae_loss_coef=0.1)
+    want = O.param_shapes(O.Cfg(model_type=mt, img_resolution=R, num_classes=ncls))
+    got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert got == {k: tuple(v) for k, v in want.items()}
+    if mt == "DiT-XL/2":
+        assert len(got) == 378 and sum(int(torch.tensor(s).prod()) for s in got.values()) == 730_541_200
+    frozen = [k for k, p in net.named_parameters() if not p.requires_grad]
+    assert sorted(frozen) == ["model.decoder_pos_embed", "model.pos_embed"]
+    assert len(DiT_models) == 15 and net.model.patch_size == 2 and net.model.extras == 0
+
+
+def test_init_matches_reference_scheme():
+    from maskdit_b200.maskdit import Precond_models, sincos_2d
+    from oracle import maskdit_oracle as O
+    net = Precond_models["edm"](8, 4, num_classes=10, model_type="DiT-S/2", use_decoder=True, mae_loss_coef=0.1)
+    sd = net.state_dict()
+    zero = [k for k, v in sd.items() if v.abs().sum() == 0]
+    for k in sd:
+        should = k.endswith(".bias") or "adaLN_modulation" in k or k.startswith(("model.final_layer.linear",
+                                                                               "model.decoder_layer.linear"))
+        assert (k in zero) == should, k
+    assert torch.allclose(sd["model.pos_embed"][0], O.sincos_pos_embed(384, 4))
+    assert torch.allclose(sincos_2d(512, 16), O.sincos_pos_embed(512, 16))
+    w = sd["model.blocks.0.attn.qkv.weight"]
+    bound = (6 / (w.shape[0] + w.shape[1])) ** 0.5
+    assert w.abs().max() <= bound + 1e-6 and w.abs().max() > 0.9 * bound
+    assert abs(sd["model.y_embedder.embedding_table.weight"].std().item() - 0.02) < 2e-3
+
+
+def test_flat_layout_plan():
+    from maskdit_b200.flat import ALIGN, FlatStore
+    from oracle import maskdit_oracle as O
+    cfg = O.Cfg(model_type="DiT-XL/2", img_resolution=32, num_classes=1000)
+    shapes = O.param_shapes(cfg)
+    st = FlatStore()
+    st.plan(shapes)
+    o, rows, hid = st.ada_w_range
+    assert o == 0 and hid == 1152 and rows == 28 * 6912 + 2304 + 8 * 3072 + 1024
+    spans = sorted((v[0], v[0] + v[1]) for v in st.offsets.values())
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 <= b0 and b0 % ALIGN == 0
+    assert st.offsets["model.pos_embed"][0] >= st.n_train  # frozen tensors sit after the trainable region
+    n_train = sum(v[1] for k, v in st.offsets.items() if not k.endswith("pos_embed"))
+    assert n_train == 730_115_216  # trainable parameter count
+
+
+def test_dp_helpers_and_schedule():
+    from maskdit_b200.train_step import lr_at, shard_batch
+    assert [shard_batch(1024, 8, r) for r in (0, 7)] == [(0, 128), (896, 1024)]
+    with pytest.raises(ValueError):
+        shard_batch(10, 4, 0)
+    assert lr_at(0, 1e-4, 1024, 10) == 0.0 and lr_at(5, 1e-4, 1024, 10) == pytest.approx(5.12e-5)
+    assert lr_at(100, 1e-4, 1024, 10) == 1e-4
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from maskdit_b200.train_step import shard_batch
+    # the step's single collective: SUM all-reduce of one flat buffer, 1/world folded in afterwards
+    torch.manual_seed(0)
+    full = torch.randn(8, 1000)                       # per-sample "gradients" of a global batch of 8
+    lo, hi = shard_batch(8, world, rank)
+    flat = full[lo:hi].sum(0)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    q.put((rank, torch.allclose(flat / world, full.sum(0) / world, atol=1e-5)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_flat_allreduce_equals_single_process():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(ok for _, ok in res) and sorted(r for r, _ in res) == [0, 1]

@@ -1,0 +1,97 @@
+"""CPU: pin the oracle (oracle/maskdit_oracle.py) against golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py ran /root/reference through the timm stand-in).  fp32 vs fp32: tight tolerances."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import maskdit_oracle as O  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SMALL = O.Cfg(model_type="DiT-S/2", img_resolution=8, num_classes=10)
+
+
+def load(name):
+    return {k: v for k, v in np.load(os.path.join(GOLD, name + ".npz")).items()}
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_tables_match_reference():
+    g = load("tables")
+    for D, grid in ((1152, 16), (512, 16), (384, 4), (512, 4), (1152, 32)):
+        step = max(1, grid * grid // 16)
+        np.testing.assert_allclose(O.sincos_pos_embed(D, grid).numpy()[::step], g[f"pos_{D}_{grid}"], atol=1e-6)
+    np.testing.assert_allclose(O.timestep_embedding(t(g["tfreq_in"]), 256).numpy(), g["tfreq"], atol=1e-6)
+    for L, r in ((256, 0.5), (1024, 0.5), (256, 0.75), (16, 0.5)):
+        md = O.mask_from_noise(t(g[f"mask_noise_{L}_{r}"]), r)
+        for k, v in md.items():
+            assert np.array_equal(v.numpy(), g[f"mask_{k}_{L}_{r}"]), (L, r, k)
+
+
+@pytest.mark.parametrize("name", ["s2_train_mask", "s2_train_nomask"])
+def test_train_loss_and_grads_match_reference(name):
+    g = load(name)
+    sd = {k: v.requires_grad_(not k.endswith("pos_embed")) for k, v in O.make_state_dict(SMALL, 1).items()}
+    mr = float(g["mask_ratio"])
+    md = O.mask_from_noise(t(g["mask_noise"]), mr) if mr > 0 else None
+    if md is not None:
+        for k in ("mask", "ids_keep", "ids_restore"):
+            assert np.array_equal(md[k].numpy(), g[k])
+    loss, D = O.edm_loss(sd, SMALL, t(g["images"]), t(g["labels"]), t(g["rnd_normal"]), t(g["noise_unit"]), md,
+                         SMALL.mae_loss_coef)
+    np.testing.assert_allclose(loss.detach().numpy(), g["loss"], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(D.detach().numpy(), g["D"], rtol=1e-4, atol=2e-5)
+    loss.mean().backward()
+    checked = 0
+    for k, v in g.items():
+        if k.startswith("grad/"):
+            gg = sd[k[5:]].grad  # None == zero gradient (reference: "+ 0 * sum(mask_token)", loss.py:57-58)
+            gg = np.zeros_like(v) if gg is None else gg.numpy()
+            np.testing.assert_allclose(gg, v, rtol=2e-3, atol=1e-6, err_msg=k)
+            checked += 1
+        elif k.startswith("gnorm/"):
+            got = sd[k[6:]].grad
+            got = 0.0 if got is None else got.double().norm().item()
+            assert abs(got - float(v)) <= 2e-4 * (float(v) + 1e-9) + 1e-9, (k, got, float(v))
+            checked += 1
+        elif k.startswith("gslice/"):
+            gg = sd[k[7:]].grad
+            np.testing.assert_allclose(gg.reshape(gg.shape[0], -1)[:4, :8].numpy(), v, rtol=2e-3, atol=1e-6)
+    assert checked > 100
+
+
+def test_eval_cfg_and_sampler_match_reference():
+    g = load("s2_eval")
+    sd = O.make_state_dict(SMALL, 1)
+    with torch.no_grad():
+        plain = O.edm_precond(sd, SMALL, t(g["images"]), t(g["sigma"]), t(g["labels"]), training=False)
+        np.testing.assert_allclose(plain.numpy(), g["D_plain"], rtol=1e-4, atol=2e-5)
+        cfg = O.edm_precond(sd, SMALL, t(g["images"]), torch.tensor(1.7, dtype=torch.float64), t(g["labels"]),
+                            cfg_scale=1.5, training=False)
+        np.testing.assert_allclose(cfg.numpy(), g["D_cfg"], rtol=1e-4, atol=2e-5)
+        lab = t(g["labels"])
+        z, evals = O.edm_sampler(lambda x, s: O.edm_precond(sd, SMALL, x, s, lab, cfg_scale=1.5, training=False),
+                                 t(g["latents"]))
+    assert len(evals) == 35  # 2N-1 network evaluations
+    np.testing.assert_allclose(np.array(evals), g["sampler_sigmas"], rtol=1e-12)
+    np.testing.assert_allclose(z.numpy(), g["z"], rtol=1e-3, atol=1e-4)
+
+
+def test_xl2_config1_forward_matches_reference():
+    """BASELINE config 1: MaskDiT-XL/2 single forward, batch 2, 32x32x4 latents, mask_ratio 0.5, fp32 on CPU."""
+    g = load("xl2_c1_fwd")
+    cfg = O.Cfg(model_type="DiT-XL/2", img_resolution=32, num_classes=1000)
+    sd = O.make_state_dict(cfg, 1)
+    assert sum(v.numel() for v in sd.values()) == 730_541_200
+    md = O.mask_from_noise(t(g["mask_noise"]), 0.5)
+    with torch.no_grad():
+        loss, D = O.edm_loss(sd, cfg, t(g["images"]), t(g["labels"]), t(g["rnd_normal"]), t(g["noise_unit"]), md,
+                             cfg.mae_loss_coef)
+    np.testing.assert_allclose(loss.numpy(), g["loss"], rtol=1e-4)
+    np.testing.assert_allclose(D.numpy(), g["D"], rtol=1e-3, atol=1e-4)

@@ -95,7 +95,13 @@ def exported_symbols():
     return ["mdt_status_string", "mdt_abi_version", *_SIGS.keys()]
 
 
-def check(status: int, what: str):
+LAUNCHES = 0  # kernels launched through the C ABI (bench.py reports it as gpu_launches)
+GEMM_PROFILE = None  # when a list: gemm() appends (flops, start_event, end_event) per launch (bench.py roofline)
+
+
+def check(status: int, what: str, n_kernels: int = 1):
+    global LAUNCHES
+    LAUNCHES += n_kernels
     if status != 0:
         msg = lib().mdt_status_string(status).decode()
         raise MdtError(f"{what} failed: {msg} (status {status})")
@@ -136,5 +142,12 @@ def gemm(A, B, M, N, K, *, lda=None, ldb=None, a_mn=False, b_mn=False, epi=EPI_S
     a.gate, a.ld_gate = ptr(gate), ld_gate
     a.rows_per_group = rows_per_group
     a.block_n = block_n
+    if GEMM_PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib().mdt_gemm_bf16(ctypes.byref(a), stream_ptr()), "mdt_gemm_bf16")
+        e1.record()
+        GEMM_PROFILE.append((2.0 * M * N * K, e0, e1))
+        return out
     check(lib().mdt_gemm_bf16(ctypes.byref(a), stream_ptr()), "mdt_gemm_bf16")
     return out

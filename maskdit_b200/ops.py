@@ -126,7 +126,7 @@ def attention_bwd(qkv, out, dout, lse, B, T, H, dh):
     _c(qkv, bf16), _c(out, bf16), _c(dout, bf16), _c(lse, f32)
     dqkv = torch.empty_like(qkv)
     check(lib().mdt_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, T, H, dh, stream_ptr()),
-          "mdt_attention_bwd")
+          "mdt_attention_bwd", 2)
     return dqkv
 
 

@@ -38,9 +38,11 @@ struct GemmCfg {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192 ? 5 : 6);
+  static constexpr int kStages = (BLOCK_N == 128) ? 6 : 4;
+  static_assert(kStages * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 8 * 32 * 33 * 4 + 1280 <= 232448, "smem budget");
   static constexpr int kTmemCols = (2 * BLOCK_N > 256) ? 512 : 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = kNumEpiWarps * 32 * 33 * 4;  // per-warp 32x33 fp32 transpose tiles
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct UnitSched {
@@ -85,118 +87,72 @@ struct UnitSched {
   MDT_DEVINL int n_tile() const { return cur_tile % num_n_tiles; }
 };
 
-// ---- fused epilogue on a 32-column chunk held by one thread (one output row) -------------------------------
-MDT_DEVINL void store_bf16x32(__nv_bfloat16* dst, const float* v, int ncols) {
-  if (ncols == 32) {
-    uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 q;
-      q.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
-      q.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-      q.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-      q.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
-      d[i] = q;
-    }
-  } else {
-    for (int i = 0; i < ncols; ++i) dst[i] = __float2bfloat16_rn(v[i]);
-  }
-}
-MDT_DEVINL void store_f32x32(float* dst, const float* v, int ncols) {
-  if (ncols == 32) {
-    float4* d = reinterpret_cast<float4*>(dst);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  } else {
-    for (int i = 0; i < ncols; ++i) dst[i] = v[i];
-  }
-}
-MDT_DEVINL void load_f32x32(const float* src, float* v, int ncols) {
-  if (ncols == 32) {
-    const float4* s = reinterpret_cast<const float4*>(src);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 q = s[i];
-      v[4 * i] = q.x, v[4 * i + 1] = q.y, v[4 * i + 2] = q.z, v[4 * i + 3] = q.w;
-    }
-  } else {
-    for (int i = 0; i < 32; ++i) v[i] = (i < ncols) ? src[i] : 0.f;
-  }
-}
-MDT_DEVINL void load_bf16x32(const __nv_bfloat16* src, float* v, int ncols) {
-  if (ncols == 32) {
-    const uint4* s = reinterpret_cast<const uint4*>(src);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 q = s[i];
-      v[8 * i + 0] = bf16_lo(q.x), v[8 * i + 1] = bf16_hi(q.x);
-      v[8 * i + 2] = bf16_lo(q.y), v[8 * i + 3] = bf16_hi(q.y);
-      v[8 * i + 4] = bf16_lo(q.z), v[8 * i + 5] = bf16_hi(q.z);
-      v[8 * i + 6] = bf16_lo(q.w), v[8 * i + 7] = bf16_hi(q.w);
-    }
-  } else {
-    for (int i = 0; i < 32; ++i) v[i] = (i < ncols) ? __bfloat162float(src[i]) : 0.f;
-  }
-}
+// ---- fused epilogue ---------------------------------------------------------------------------------------
+// tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns).  Writing rows straight to global
+// would make every warp store touch 32 different 128-byte lines; instead the 32x32 fp32 chunk is transposed through
+// a per-warp smem staging tile (row stride 33 words: conflict-free both ways) so that in the second phase
+// lane == column: every global load/store/atomic of a warp instruction covers ONE contiguous row segment
+// (128 B fp32 / 64 B bf16), and bias/gate/residual/aux reads are coalesced the same way.
+constexpr int kStgStride = 33;
+constexpr int kStgFloats = 32 * kStgStride;
 
-MDT_DEVINL void epilogue_chunk(const GemmParams& p, int row, int col0, int ncols, float* acc, bool partial) {
-  const size_t o = static_cast<size_t>(row) * p.ldo + col0;
-  if (p.epi == EPI_ATOMIC || partial) {
-    float* out = reinterpret_cast<float*>(p.out) + o;
-    for (int i = 0; i < ncols; ++i) atomicAdd(out + i, acc[i]);
-    return;
-  }
-  if (p.bias) {
-    float b[32];
-    load_f32x32(p.bias + col0, b, ncols);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] += b[i];
-  }
+MDT_DEVINL void epilogue_rows(const GemmParams& p, const float* stg, int row_base, int nrows, int col, bool col_ok,
+                              int lane) {
+  if (!col_ok) return;
+  const float bias_v = p.bias ? p.bias[col] : 0.f;
   switch (p.epi) {
+    case EPI_ATOMIC: {
+      float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll 4
+      for (int r = 0; r < nrows; ++r)
+        atomicAdd(out + static_cast<size_t>(row_base + r) * p.ldo + col, stg[r * kStgStride + lane]);
+    } break;
     case EPI_STORE: {
-      if (p.resid) {
-        float r[32];
-        load_f32x32(p.resid + static_cast<size_t>(row) * p.ld_resid + col0, r, ncols);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] += r[i];
+#pragma unroll 4
+      for (int r = 0; r < nrows; ++r) {
+        const size_t row = row_base + r;
+        float v = stg[r * kStgStride + lane] + bias_v;
+        if (p.resid) v += p.resid[row * p.ld_resid + col];
+        if (p.act == ACT_SILU) v = silu(v);
+        if (p.out_fp32)
+          reinterpret_cast<float*>(p.out)[row * p.ldo + col] = v;
+        else
+          reinterpret_cast<__nv_bfloat16*>(p.out)[row * p.ldo + col] = __float2bfloat16_rn(v);
       }
-      if (p.act == ACT_SILU) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = silu(acc[i]);
-      }
-      if (p.out_fp32)
-        store_f32x32(reinterpret_cast<float*>(p.out) + o, acc, ncols);
-      else
-        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out) + o, acc, ncols);
     } break;
     case EPI_GELU: {
       // pre-activation is rounded to bf16 first (as a bf16 nn.Linear output would be), GELU on the rounded value
-      __nv_bfloat16* pre = reinterpret_cast<__nv_bfloat16*>(p.aux) + static_cast<size_t>(row) * p.ld_aux + col0;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] = round_bf16(acc[i]);
-      if (p.aux) store_bf16x32(pre, acc, ncols);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] = gelu_tanh(acc[i]);
-      store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out) + o, acc, ncols);
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+      __nv_bfloat16* aux = reinterpret_cast<__nv_bfloat16*>(p.aux);
+#pragma unroll 4
+      for (int r = 0; r < nrows; ++r) {
+        const size_t row = row_base + r;
+        const __nv_bfloat16 pre = __float2bfloat16_rn(stg[r * kStgStride + lane] + bias_v);
+        if (aux) aux[row * p.ld_aux + col] = pre;
+        out[row * p.ldo + col] = __float2bfloat16_rn(gelu_tanh(__bfloat162float(pre)));
+      }
     } break;
     case EPI_GATE_RESID: {
-      if (p.aux)
-        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.aux) + static_cast<size_t>(row) * p.ld_aux + col0, acc,
-                      ncols);
-      float g[32], r[32];
-      load_f32x32(p.gate + static_cast<size_t>(row / p.rows_per_group) * p.ld_gate + col0, g, ncols);
-      load_f32x32(p.resid + static_cast<size_t>(row) * p.ld_resid + col0, r, ncols);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] = fmaf(g[i], acc[i], r[i]);
-      store_f32x32(reinterpret_cast<float*>(p.out) + o, acc, ncols);
+      float* out = reinterpret_cast<float*>(p.out);
+      __nv_bfloat16* aux = reinterpret_cast<__nv_bfloat16*>(p.aux);
+#pragma unroll 4
+      for (int r = 0; r < nrows; ++r) {
+        const size_t row = row_base + r;
+        const float y = stg[r * kStgStride + lane] + bias_v;
+        if (aux) aux[row * p.ld_aux + col] = __float2bfloat16_rn(y);
+        const float g = p.gate[static_cast<size_t>(row / p.rows_per_group) * p.ld_gate + col];
+        out[row * p.ldo + col] = fmaf(g, y, p.resid[row * p.ld_resid + col]);
+      }
     } break;
     case EPI_DGELU: {
-      float h[32];
-      load_bf16x32(reinterpret_cast<const __nv_bfloat16*>(p.aux) + static_cast<size_t>(row) * p.ld_aux + col0, h,
-                   ncols);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] *= gelu_tanh_grad(h[i]);
-      store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out) + o, acc, ncols);
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+      const __nv_bfloat16* aux = reinterpret_cast<const __nv_bfloat16*>(p.aux);
+#pragma unroll 4
+      for (int r = 0; r < nrows; ++r) {
+        const size_t row = row_base + r;
+        const float h = __bfloat162float(aux[row * p.ld_aux + col]);
+        out[row * p.ldo + col] = __float2bfloat16_rn(stg[r * kStgStride + lane] * gelu_tanh_grad(h));
+      }
     } break;
     default: break;
   }
@@ -211,7 +167,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_tiles = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  float* staging = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;           // [kStages]  MMA -> TMA
   uint64_t* tmem_full_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue
@@ -316,10 +273,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t aphase = 0;
     while (sched.next()) {
       const int m0 = sched.m_tile() * BLOCK_M, n0 = sched.n_tile() * BLOCK_N;
-      const bool partial = p.streamk != 0;
       mbar_wait(&tmem_full_bar[as], aphase);
       tcgen05_fence_after();
-      const int row = m0 + lane_group * 32 + lane;
+      const int row_base = m0 + lane_group * 32;
+      int nrows = p.M - row_base;
+      nrows = nrows > 32 ? 32 : nrows;
+      float* stg = staging + ew * kStgFloats;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * BLOCK_N +
                              col_half * kColsPerWarp;
 #pragma unroll 1
@@ -328,13 +287,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tmem_ld_32x32b_x32(taddr + c, r);
         tcgen05_wait_ld();
         const int col0 = n0 + col_half * kColsPerWarp + c;
-        int ncols = p.N - col0;
-        ncols = ncols > 32 ? 32 : ncols;
-        if (row < p.M && ncols > 0) {
-          float acc[32];
+        if (nrows > 0 && col0 < p.N) {  // warp-uniform
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(r[i]);
-          epilogue_chunk(p, row, col0, ncols, acc, partial);
+          for (int j = 0; j < 32; ++j) stg[lane * kStgStride + j] = __uint_as_float(r[j]);
+          __syncwarp();
+          epilogue_rows(p, stg, row_base, nrows, col0 + lane, col0 + lane < p.N, lane);
+          __syncwarp();
         }
       }
       tcgen05_fence_before();

@@ -137,3 +137,44 @@ def test_gloo_world2_flat_allreduce_equals_single_process():
     for p in procs:
         p.join(60)
     assert all(ok for _, ok in res) and sorted(r for r, _ in res) == [0, 1]
+
+
+YAML = """
+data: {dataset: imagenet256-latent, category: lmdb, resolution: 32, num_channels: 4, root: ../data, feat_path: None}
+model:
+  precond: edm
+  model_type: DiT-XL/2
+  in_size: 32
+  in_channels: 4
+  num_classes: 1000
+  use_decoder: True
+  ext_feature_dim: 0
+  pad_cls_token: False
+  mask_ratio: 0.5
+  mask_ratio_fn: constant
+  mask_ratio_min: 0
+  mae_loss_coef: 0.1
+  class_dropout_prob: 0.1
+train: {tf32: False, amp: True, batchsize: 128, grad_accum: 1, epochs: 2800, lr: 0.0001, lr_rampup_kimg: 0,
+        xflip: False, max_num_steps: 2000000}
+log: {log_every: 500, ckpt_every: 50_000, tag: pretrain}
+"""
+
+
+def test_config_schema_and_mask_schedule():
+    """The reference YAML schema (configs/train/imagenet256-latent.yaml) parses with PyYAML; schedules follow
+    get_mask_ratio_fn (train_utils/helper.py:9-27) incl. the `cos4` alias of the finetune config."""
+    import math
+    from maskdit_b200.config import load_config, mask_ratio_schedule, parse_float_none, parse_int_list
+    cfg = load_config(YAML)
+    assert cfg.model.model_type == "DiT-XL/2" and cfg.train.batchsize == 128 and cfg.data.feat_path is None
+    assert cfg.log.ckpt_every == 50000 and cfg.model.get("self_cond") is None
+    assert mask_ratio_schedule("constant", 0.5)(0.3) == 0.5
+    for name in ("cosine4", "cos4"):
+        f = mask_ratio_schedule(name, 0.5, 0.1)
+        assert f(0.25) == pytest.approx(0.4 * math.cos(math.pi * 0.125) ** 4 + 0.1)
+    assert mask_ratio_schedule("linear", 0.5, 0.1)(0.5) == pytest.approx(0.3)
+    assert mask_ratio_schedule("exp", 0.5, 0.0)(1.0) == pytest.approx(0.5 * math.exp(-7))
+    with pytest.raises(ValueError):
+        mask_ratio_schedule("bogus")
+    assert parse_int_list("1,2,5-8") == [1, 2, 5, 6, 7, 8] and parse_float_none("None") is None

@@ -22,8 +22,9 @@
 #include "common.cuh"
 #include "gemm.h"
 
+#include <stdlib.h>
+
 #include <mutex>
-#include <unordered_map>
 
 namespace mdt {
 
@@ -33,16 +34,22 @@ constexpr int UMMA_K = 16;
 constexpr int kNumEpiWarps = 8;
 constexpr int kNumThreads = 128 + kNumEpiWarps * 32;  // 384
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CG>
 struct GemmCfg {
+  // CG = 1: one CTA per 128 x BLOCK_N tile.  CG = 2: an SM pair per 256 x BLOCK_N tile (tcgen05 cta_group::2):
+  // each CTA stages its own 128 rows of A and HALF of the B tile, which halves the smem fill+read traffic per
+  // MMA flop (a single-CTA 128x256 tile needs 187 B/clk of smem bandwidth at full tensor rate, the SM has 128).
+  static constexpr int kBRows = BLOCK_N / CG;
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kBBytes = kBRows * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192 ? 5 : 6);
-  static_assert(kStages * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 8 * 16 * 36 * 4 + 1280 <= 232448, "smem budget");
-  static constexpr int kTmemCols = (2 * BLOCK_N > 256) ? 512 : 256;
   static constexpr int kStagingBytes = kNumEpiWarps * 16 * 36 * 4;  // per-warp 16x36 fp32 transpose tiles
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kFixed = kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagesFit = (232448 - kFixed) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+  static constexpr int kTmemCols = (2 * BLOCK_N > 256) ? 512 : 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixed;
+  static_assert(kStages >= 3, "pipeline too shallow");
 };
 
 struct UnitSched {
@@ -51,18 +58,19 @@ struct UnitSched {
   long long it, it_end;  // stream-K: global iteration range
   int tile, grid;        // tile mode
   int cur_tile, kb0, kb1;
-  MDT_DEVINL void init(const GemmParams& p) {
+  MDT_DEVINL void init(const GemmParams& p, int cg) {
     mode = p.streamk;
     num_kb = p.num_kb;
     num_n_tiles = p.num_n_tiles;
     num_tiles = p.num_m_tiles * p.num_n_tiles;
-    grid = gridDim.x;
+    grid = gridDim.x / cg;              // CTA groups; both CTAs of a pair walk the same unit sequence
+    const int gid = blockIdx.x / cg;
     if (mode) {
       long long total = static_cast<long long>(num_tiles) * num_kb;
-      it = total * blockIdx.x / grid;
-      it_end = total * (blockIdx.x + 1) / grid;
+      it = total * gid / grid;
+      it_end = total * (gid + 1) / grid;
     } else {
-      tile = blockIdx.x;
+      tile = gid;
     }
   }
   MDT_DEVINL bool next() {
@@ -177,25 +185,28 @@ MDT_DEVINL void epilogue_scalar(const GemmParams& p, size_t row, int col, float 
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, CG>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int TILE_M = BLOCK_M * CG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_tiles = smem;
   float* staging = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
-  uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA
-  uint64_t* empty_bar = bars + kStages;           // [kStages]  MMA -> TMA
-  uint64_t* tmem_full_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]        epilogue -> MMA
+  uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA        (CG=2: the leader's is used)
+  uint64_t* empty_bar = bars + kStages;           // [kStages]  MMA -> TMA        (CG=2: commit multicast to both)
+  uint64_t* tmem_full_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue   (CG=2: commit multicast to both)
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]        epilogue -> MMA   (CG=2: both CTAs arrive on leader)
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -203,56 +214,68 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], CG);   // leader: arrive.expect_tx ; peer: plain arrive after issuing its loads
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], kNumEpiWarps);
+      mbar_init(&tmem_empty_bar[s], kNumEpiWarps * CG);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_base_smem);
+  if (warp == 2) {
+    if constexpr (CG == 2) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_base_smem);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_base_smem);
+  }
+  __syncwarp();
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
   UnitSched sched;
-  sched.init(p);
+  sched.init(p, CG);
 
   if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA) =====================
     int stage = 0;
     uint32_t phase = 0;
     while (sched.next()) {
-      const int m0 = sched.m_tile() * BLOCK_M, n0 = sched.n_tile() * BLOCK_N;
+      const int m0 = sched.m_tile() * TILE_M + cta_rank * BLOCK_M;
+      const int n0 = sched.n_tile() * BLOCK_N + cta_rank * Cfg::kBRows;
       for (int kb = sched.kb0; kb < sched.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem_tiles + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kABytes;
-        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
         const int k0 = kb * BLOCK_K;
+        auto load = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
+          if constexpr (CG == 2) tma_load_2d_2sm(m, &full_bar[stage], dst, c0, c1);
+          else tma_load_2d(m, &full_bar[stage], dst, c0, c1);
+        };
         if constexpr (!A_MN) {
-          tma_load_2d(&tmap_a, &full_bar[stage], sa, k0, m0);  // box {64 k, 128 rows}
+          load(&tmap_a, sa, k0, m0);  // box {64 k, 128 rows}
         } else {
 #pragma unroll
           for (int j = 0; j < BLOCK_M / 64; ++j)  // boxes {64 mn, 64 k}
-            tma_load_2d(&tmap_a, &full_bar[stage], sa + j * (64 * BLOCK_K * 2), m0 + j * 64, k0);
+            load(&tmap_a, sa + j * (64 * BLOCK_K * 2), m0 + j * 64, k0);
         }
         if constexpr (!B_MN) {
-          tma_load_2d(&tmap_b, &full_bar[stage], sb, k0, n0);  // box {64 k, BLOCK_N rows}
+          load(&tmap_b, sb, k0, n0);  // box {64 k, BLOCK_N / CG rows}
         } else {
 #pragma unroll
-          for (int j = 0; j < BLOCK_N / 64; ++j)
-            tma_load_2d(&tmap_b, &full_bar[stage], sb + j * (64 * BLOCK_K * 2), n0 + j * 64, k0);
+          for (int j = 0; j < Cfg::kBRows / 64; ++j)
+            load(&tmap_b, sb + j * (64 * BLOCK_K * 2), n0 + j * 64, k0);
+        }
+        if constexpr (CG == 2) {
+          if (!leader) mbar_arrive_cluster(&full_bar[stage], 0);
         }
         if (++stage == kStages) stage = 0, phase ^= 1;
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -274,16 +297,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                    : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
           const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), 64 * BLOCK_K * 2, 1024)
                                    : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
-          umma_bf16(tmem_d, da, db, idesc, (kb > sched.kb0 || k > 0) ? 1u : 0u);
+          const uint32_t acc = (kb > sched.kb0 || k > 0) ? 1u : 0u;
+          if constexpr (CG == 2) umma_bf16_2sm(tmem_d, da, db, idesc, acc);
+          else umma_bf16(tmem_d, da, db, idesc, acc);
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+        // frees the smem slot (in both CTAs) once these MMAs retire
+        if constexpr (CG == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
         if (++stage == kStages) stage = 0, phase ^= 1;
       }
-      umma_commit(&tmem_full_bar[as]);  // accumulator complete -> epilogue
+      // accumulator complete -> epilogue warps (of both CTAs)
+      if constexpr (CG == 2) umma_commit_2sm(&tmem_full_bar[as]); else umma_commit(&tmem_full_bar[as]);
       if (++as == 2) as = 0, aphase ^= 1;
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
+    // ===================== epilogue (every CTA: its own 128 accumulator rows) =====================
     const int ew = warp - 4;
     const int lane_group = warp & 3;           // tcgen05.ld: warp w may touch TMEM lanes 32*(w%4)..+31
     const int col_half = ew >> 2;              // 0/1
@@ -291,7 +318,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int as = 0;
     uint32_t aphase = 0;
     while (sched.next()) {
-      const int m0 = sched.m_tile() * BLOCK_M, n0 = sched.n_tile() * BLOCK_N;
+      const int m0 = sched.m_tile() * TILE_M + cta_rank * BLOCK_M, n0 = sched.n_tile() * BLOCK_N;
       mbar_wait(&tmem_full_bar[as], aphase);
       tcgen05_fence_after();
       const int row_base = m0 + lane_group * 32;
@@ -343,16 +370,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+        else mbar_arrive(&tmem_empty_bar[as]);
+      }
       if (++as == 2) as = 0, aphase ^= 1;
     }
   }
 
+  __syncwarp();  // role branches above are per-lane; reconverge before the .aligned barriers below
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -402,21 +434,22 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, int CG>
 static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, CG>;
+  constexpr int TILE_M = BLOCK_M * CG;
   CUtensorMap ta, tb;
   int rc;
   // A: K-major stored [M, K] ld=lda -> dims {K, M}, box {64, 128}; MN-major stored [K, M] -> dims {M, K}, box {64, 64}
   rc = A_MN ? make_tmap(&ta, a.A, a.M, a.K, a.lda, 64, 64) : make_tmap(&ta, a.A, a.K, a.M, a.lda, 64, BLOCK_M);
   if (rc) return rc;
-  rc = B_MN ? make_tmap(&tb, a.B, a.N, a.K, a.ldb, 64, 64) : make_tmap(&tb, a.B, a.K, a.N, a.ldb, 64, BLOCK_N);
+  rc = B_MN ? make_tmap(&tb, a.B, a.N, a.K, a.ldb, 64, 64) : make_tmap(&tb, a.B, a.K, a.N, a.ldb, 64, Cfg::kBRows);
   if (rc) return rc;
 
   GemmParams p;
   p.M = a.M, p.N = a.N, p.K = a.K;
   p.epi = a.epi, p.act = a.act;
-  p.num_m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
+  p.num_m_tiles = (a.M + TILE_M - 1) / TILE_M;
   p.num_n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
   p.num_kb = (a.K + BLOCK_K - 1) / BLOCK_K;
   p.out = a.out, p.ldo = a.ldo, p.out_fp32 = a.out_fp32;
@@ -425,43 +458,68 @@ static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
   p.resid = a.resid, p.ld_resid = a.ld_resid;
   p.gate = a.gate, p.ld_gate = a.ld_gate, p.rows_per_group = a.rows_per_group > 0 ? a.rows_per_group : 1;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int sms = num_sms();
+  const int groups = num_sms() / CG;  // CTA groups resident at once (1 CTA per SM)
   // stream-K whenever the epilogue is a pure fp32 accumulation
   p.streamk = (a.epi == EPI_ATOMIC) ? 1 : 0;
-  int grid;
-  if (p.streamk) {
-    long long total = static_cast<long long>(tiles) * p.num_kb;
-    grid = total < sms ? static_cast<int>(total) : sms;
-  } else {
-    grid = tiles < sms ? tiles : sms;
-  }
+  long long units = p.streamk ? static_cast<long long>(tiles) * p.num_kb : tiles;
+  const int grid = static_cast<int>(units < groups ? units : groups) * CG;
   if (grid <= 0) return MDT_OK;
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return MDT_ERR_CUDA;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return MDT_ERR_CUDA;
     attr_set = true;
   }
-  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kNumThreads), cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kern, ta, tb, p) != cudaSuccess) return MDT_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? MDT_OK : MDT_ERR_CUDA;
 }
 
+static int g_force_cg = 0;  // 0 = auto, 1 / 2 = forced (MDT_GEMM_CG env, for A/B measurements)
+
 template <bool A_MN, bool B_MN>
 static int dispatch_n(const mdt_gemm_args& a, cudaStream_t stream) {
-  // pick the tile width that wastes the fewest columns; ties -> wider tile
+  static bool env_read = false;
+  if (!env_read) {
+    const char* e = getenv("MDT_GEMM_CG");
+    if (e) g_force_cg = atoi(e);
+    env_read = true;
+  }
+  // SM pairs (256-row tiles) whenever there are at least two 128-row panels; single CTAs for skinny problems
+  int cg = (a.M > BLOCK_M) ? 2 : 1;
+  if (g_force_cg == 1 || g_force_cg == 2) cg = g_force_cg;
+  // pick the tile width that wastes the fewest columns; ties -> wider tile.  With an MN-major B operand a CTA of a
+  // pair stages BLOCK_N/2 columns as 64-wide TMA boxes, so 192 is not available there.
   int best = 256;
   long long best_cost = -1;
   const int cands[3] = {256, 192, 128};
   for (int c : cands) {
+    if (cg == 2 && B_MN && c == 192) continue;
     long long cost = static_cast<long long>((a.N + c - 1) / c) * c;
     if (best_cost < 0 || cost < best_cost) best = c, best_cost = cost;
   }
   if (a.block_n == 128 || a.block_n == 192 || a.block_n == 256) best = a.block_n;
+  if (cg == 2 && B_MN && best == 192) best = 128;
+  if (cg == 2) {
+    switch (best) {
+      case 256: return launch<256, A_MN, B_MN, 2>(a, stream);
+      case 192:
+        if constexpr (!B_MN) return launch<192, A_MN, B_MN, 2>(a, stream);
+        return MDT_ERR_ARG;
+      default: return launch<128, A_MN, B_MN, 2>(a, stream);
+    }
+  }
   switch (best) {
-    case 256: return launch<256, A_MN, B_MN>(a, stream);
-    case 192: return launch<192, A_MN, B_MN>(a, stream);
-    default: return launch<128, A_MN, B_MN>(a, stream);
+    case 256: return launch<256, A_MN, B_MN, 1>(a, stream);
+    case 192: return launch<192, A_MN, B_MN, 1>(a, stream);
+    default: return launch<128, A_MN, B_MN, 1>(a, stream);
   }
 }
 

@@ -90,9 +90,9 @@ MDT_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU box.
-MDT_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU box.  The slow path is kept out of
+// line so that the hot loops stay small in the instruction cache.
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
@@ -100,6 +100,11 @@ MDT_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+MDT_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -43,7 +43,7 @@ struct GemmCfg {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = kBRows * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kNumEpiWarps * 16 * 36 * 4;  // per-warp 16x36 fp32 transpose tiles
+  static constexpr int kStagingBytes = kNumEpiWarps * 32 * 36 * 4;  // per-warp 32x36 fp32 transpose tiles
   static constexpr int kFixed = kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kStagesFit = (232448 - kFixed) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
@@ -98,90 +98,111 @@ struct UnitSched {
 // ---- fused epilogue ---------------------------------------------------------------------------------------
 // tcgen05.ld hands each thread one accumulator ROW (32 consecutive fp32 columns).  Writing rows straight to global
 // makes every warp store touch 32 different 128-byte lines (ncu v1: 32 sectors/request, tensor pipe 18-50 % busy).
-// The 32x32 chunk is therefore transposed through a per-warp smem staging tile, 16 rows at a time (row stride 36
-// words: STS.128 by row-owners and LDS.128 by (row, 4-column) owners are both bank-conflict free).  In the second
-// phase lane -> (row = lane/8, 4 columns = lane%8): one warp instruction covers 4 rows x 128 contiguous bytes
-// (fp32) / 64 bytes (bf16), and bias / gate / residual / aux are read with the same coalesced vector pattern.
+// The 32x32 chunk is therefore transposed through a per-warp smem staging tile (row stride 36 words: STS.128 by
+// row owners and LDS.128 by (row, 4-column) owners are both conflict free per quarter warp).  In the second phase
+// lane -> (row = lane/8 + 4i, 4 columns = lane%8): one warp instruction covers 4 rows x 128 contiguous bytes (fp32)
+// or 64 bytes (bf16), and bias / gate / residual / aux are read with the same coalesced vector pattern.
+// The per-epilogue loops are separate template instances selected by ONE switch per chunk, so a launch only ever
+// touches the instructions of its own epilogue (ncu v3 showed the epilogue instruction-fetch bound).
 constexpr int kStgStride = 36;
-constexpr int kStgRows = 16;
-constexpr int kStgFloats = kStgRows * kStgStride;
+constexpr int kStgFloats = 32 * kStgStride;
 
 MDT_DEVINL uint2 pack4_bf16(float4 v) { return make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)); }
 MDT_DEVINL float4 unpack4_bf16(uint2 u) { return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y)); }
 
-// one row, 4 consecutive columns (col % 4 == 0, col + 4 <= N)
-MDT_DEVINL void epilogue_vec4(const GemmParams& p, size_t row, int col, float4 v, const float4& bias4) {
-  if (p.epi == EPI_ATOMIC) {
-    float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
-    atomicAdd(o + 0, v.x), atomicAdd(o + 1, v.y), atomicAdd(o + 2, v.z), atomicAdd(o + 3, v.w);
-    return;
-  }
-  v.x += bias4.x, v.y += bias4.y, v.z += bias4.z, v.w += bias4.w;
-  switch (p.epi) {
-    case EPI_STORE: {
-      if (p.resid) {
-        const float4 r = *reinterpret_cast<const float4*>(p.resid + row * p.ld_resid + col);
-        v.x += r.x, v.y += r.y, v.z += r.z, v.w += r.w;
+template <int EPI>
+MDT_DEVINL void epilogue_chunk(const GemmParams& p, const float* stg, int row_base, int nrows, int col, int lane) {
+  const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (EPI != EPI_ATOMIC && p.bias) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
+  const size_t row0 = static_cast<size_t>(row_base + rsub);
+  size_t o_out = row0 * p.ldo + col;
+  size_t o_aux = row0 * p.ld_aux + col;
+  size_t o_res = row0 * p.ld_resid + col;
+  const float* sp = stg + rsub * kStgStride + c4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i, o_out += 4 * static_cast<size_t>(p.ldo), o_aux += 4 * static_cast<size_t>(p.ld_aux),
+           o_res += 4 * static_cast<size_t>(p.ld_resid), sp += 4 * kStgStride) {
+    if (4 * i + rsub >= nrows) break;
+    float4 v = *reinterpret_cast<const float4*>(sp);
+    if constexpr (EPI == EPI_ATOMIC) {
+      float* o = reinterpret_cast<float*>(p.out) + o_out;
+      atomicAdd(o + 0, v.x), atomicAdd(o + 1, v.y), atomicAdd(o + 2, v.z), atomicAdd(o + 3, v.w);
+    } else {
+      v.x += bias4.x, v.y += bias4.y, v.z += bias4.z, v.w += bias4.w;
+      if constexpr (EPI == EPI_STORE) {
+        if (p.resid) {
+          const float4 r = *reinterpret_cast<const float4*>(p.resid + o_res);
+          v.x += r.x, v.y += r.y, v.z += r.z, v.w += r.w;
+        }
+        if (p.act == ACT_SILU) v = make_float4(silu(v.x), silu(v.y), silu(v.z), silu(v.w));
+        if (p.out_fp32)
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o_out) = v;
+        else
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o_out) = pack4_bf16(v);
+      } else if constexpr (EPI == EPI_GELU) {
+        // pre-activation is rounded to bf16 first (as a bf16 nn.Linear output would be), GELU on the rounded value
+        const uint2 pre = pack4_bf16(v);
+        if (p.aux) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.aux) + o_aux) = pre;
+        const float4 h = unpack4_bf16(pre);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o_out) =
+            pack4_bf16(make_float4(gelu_tanh(h.x), gelu_tanh(h.y), gelu_tanh(h.z), gelu_tanh(h.w)));
+      } else if constexpr (EPI == EPI_GATE_RESID) {
+        if (p.aux) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.aux) + o_aux) = pack4_bf16(v);
+        const size_t b = (row0 + 4 * i) / p.rows_per_group;
+        const float4 g = *reinterpret_cast<const float4*>(p.gate + b * p.ld_gate + col);
+        const float4 r = *reinterpret_cast<const float4*>(p.resid + o_res);
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o_out) =
+            make_float4(fmaf(g.x, v.x, r.x), fmaf(g.y, v.y, r.y), fmaf(g.z, v.z, r.z), fmaf(g.w, v.w, r.w));
+      } else if constexpr (EPI == EPI_DGELU) {
+        const float4 h = unpack4_bf16(
+            *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + o_aux));
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o_out) =
+            pack4_bf16(make_float4(v.x * gelu_tanh_grad(h.x), v.y * gelu_tanh_grad(h.y), v.z * gelu_tanh_grad(h.z),
+                                   v.w * gelu_tanh_grad(h.w)));
       }
-      if (p.act == ACT_SILU) v = make_float4(silu(v.x), silu(v.y), silu(v.z), silu(v.w));
-      if (p.out_fp32)
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col) = v;
-      else
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col) = pack4_bf16(v);
-    } break;
-    case EPI_GELU: {
-      // pre-activation is rounded to bf16 first (as a bf16 nn.Linear output would be), GELU on the rounded value
-      const uint2 pre = pack4_bf16(v);
-      if (p.aux) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.aux) + row * p.ld_aux + col) = pre;
-      const float4 h = unpack4_bf16(pre);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col) =
-          pack4_bf16(make_float4(gelu_tanh(h.x), gelu_tanh(h.y), gelu_tanh(h.z), gelu_tanh(h.w)));
-    } break;
-    case EPI_GATE_RESID: {
-      if (p.aux) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.aux) + row * p.ld_aux + col) = pack4_bf16(v);
-      const float4 g = *reinterpret_cast<const float4*>(p.gate + (row / p.rows_per_group) * p.ld_gate + col);
-      const float4 r = *reinterpret_cast<const float4*>(p.resid + row * p.ld_resid + col);
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col) =
-          make_float4(fmaf(g.x, v.x, r.x), fmaf(g.y, v.y, r.y), fmaf(g.z, v.z, r.z), fmaf(g.w, v.w, r.w));
-    } break;
-    case EPI_DGELU: {
-      const float4 h = unpack4_bf16(
-          *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + row * p.ld_aux + col));
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col) =
-          pack4_bf16(make_float4(v.x * gelu_tanh_grad(h.x), v.y * gelu_tanh_grad(h.y), v.z * gelu_tanh_grad(h.z),
-                                 v.w * gelu_tanh_grad(h.w)));
-    } break;
-    default: break;
+    }
   }
 }
 
-// ragged right edge (N % 4 != 0): element-wise, same arithmetic
-MDT_DEVINL void epilogue_scalar(const GemmParams& p, size_t row, int col, float v) {
-  if (p.epi == EPI_ATOMIC) {
-    atomicAdd(reinterpret_cast<float*>(p.out) + row * p.ldo + col, v);
-    return;
-  }
-  if (p.bias) v += p.bias[col];
-  __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col;
-  float* o32 = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
-  __nv_bfloat16* aux = reinterpret_cast<__nv_bfloat16*>(p.aux) + row * p.ld_aux + col;
-  switch (p.epi) {
-    case EPI_STORE:
-      if (p.resid) v += p.resid[row * p.ld_resid + col];
-      if (p.act == ACT_SILU) v = silu(v);
-      if (p.out_fp32) *o32 = v; else *o16 = __float2bfloat16_rn(v);
-      break;
-    case EPI_GELU: {
-      const __nv_bfloat16 pre = __float2bfloat16_rn(v);
-      if (p.aux) *aux = pre;
-      *o16 = __float2bfloat16_rn(gelu_tanh(__bfloat162float(pre)));
-    } break;
-    case EPI_GATE_RESID:
-      if (p.aux) *aux = __float2bfloat16_rn(v);
-      *o32 = fmaf(p.gate[(row / p.rows_per_group) * p.ld_gate + col], v, p.resid[row * p.ld_resid + col]);
-      break;
-    case EPI_DGELU: *o16 = __float2bfloat16_rn(v * gelu_tanh_grad(__bfloat162float(*aux))); break;
-    default: break;
+// ragged right edge (N % 4 != 0 inside this 4-column group): element-wise, same arithmetic, cold path
+__device__ __noinline__ void epilogue_ragged(const GemmParams& p, const float* stg, int row_base, int nrows, int col,
+                                             int lane) {
+  const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+  for (int i = 0; i < 8; ++i) {
+    const int rr = 4 * i + rsub;
+    if (rr >= nrows) break;
+    const size_t row = static_cast<size_t>(row_base + rr);
+    for (int j = 0; j < 4 && col + j < p.N; ++j) {
+      float v = stg[rr * kStgStride + c4 + j];
+      const int c = col + j;
+      if (p.epi == EPI_ATOMIC) {
+        atomicAdd(reinterpret_cast<float*>(p.out) + row * p.ldo + c, v);
+        continue;
+      }
+      if (p.bias) v += p.bias[c];
+      __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + c;
+      float* o32 = reinterpret_cast<float*>(p.out) + row * p.ldo + c;
+      __nv_bfloat16* aux = reinterpret_cast<__nv_bfloat16*>(p.aux) + row * p.ld_aux + c;
+      switch (p.epi) {
+        case EPI_STORE:
+          if (p.resid) v += p.resid[row * p.ld_resid + c];
+          if (p.act == ACT_SILU) v = silu(v);
+          if (p.out_fp32) *o32 = v; else *o16 = __float2bfloat16_rn(v);
+          break;
+        case EPI_GELU: {
+          const __nv_bfloat16 pre = __float2bfloat16_rn(v);
+          if (p.aux) *aux = pre;
+          *o16 = __float2bfloat16_rn(gelu_tanh(__bfloat162float(pre)));
+        } break;
+        case EPI_GATE_RESID:
+          if (p.aux) *aux = __float2bfloat16_rn(v);
+          *o32 = fmaf(p.gate[(row / p.rows_per_group) * p.ld_gate + c], v, p.resid[row * p.ld_resid + c]);
+          break;
+        case EPI_DGELU: *o16 = __float2bfloat16_rn(v * gelu_tanh_grad(__bfloat162float(*aux))); break;
+        default: break;
+      }
+    }
   }
 }
 
@@ -334,38 +355,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tcgen05_wait_ld();
         const int col0 = n0 + col_half * kColsPerWarp + c;
         if (nrows > 0 && col0 < p.N) {  // warp-uniform
-          const int c4 = (lane & 7) * 4, col = col0 + c4;
-          const bool vec_ok = col + 4 <= p.N;
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias && vec_ok && p.epi != EPI_ATOMIC) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
+          float4* dst = reinterpret_cast<float4*>(stg + lane * kStgStride);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if ((lane >> 4) == h) {
-              float4* dst = reinterpret_cast<float4*>(stg + (lane & 15) * kStgStride);
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                     __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+          for (int q = 0; q < 8; ++q)
+            dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                 __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+          __syncwarp();
+          const int col = col0 + (lane & 7) * 4;
+          if (col + 4 <= p.N) {
+            switch (p.epi) {
+              case EPI_STORE: epilogue_chunk<EPI_STORE>(p, stg, row_base, nrows, col, lane); break;
+              case EPI_GELU: epilogue_chunk<EPI_GELU>(p, stg, row_base, nrows, col, lane); break;
+              case EPI_GATE_RESID: epilogue_chunk<EPI_GATE_RESID>(p, stg, row_base, nrows, col, lane); break;
+              case EPI_DGELU: epilogue_chunk<EPI_DGELU>(p, stg, row_base, nrows, col, lane); break;
+              case EPI_ATOMIC: epilogue_chunk<EPI_ATOMIC>(p, stg, row_base, nrows, col, lane); break;
+              default: break;
             }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rloc = 4 * i + (lane >> 3);
-              const int rr = h * kStgRows + rloc;
-              if (rr < nrows) {
-                const float4 v = *reinterpret_cast<const float4*>(stg + rloc * kStgStride + c4);
-                const size_t row = static_cast<size_t>(row_base + rr);
-                if (vec_ok) {
-                  epilogue_vec4(p, row, col, v, bias4);
-                } else {
-                  const float e[4] = {v.x, v.y, v.z, v.w};
-                  for (int j = 0; j < 4; ++j)
-                    if (col + j < p.N) epilogue_scalar(p, row, col + j, e[j]);
-                }
-              }
-            }
-            __syncwarp();
+          } else if (col < p.N) {
+            epilogue_ragged(p, stg, row_base, nrows, col, lane);
           }
+          __syncwarp();
         }
       }
       tcgen05_fence_before();

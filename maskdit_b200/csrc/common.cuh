@@ -62,6 +62,51 @@ MDT_DEVINL float silu_grad(float x) {
   return s * (1.f + x * (1.f - s));
 }
 
+// explicit shared-state-space vector accesses (pointers carved out of the dynamic smem blob via integer casts
+// degrade to generic LD/ST otherwise)
+MDT_DEVINL void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+MDT_DEVINL float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+MDT_DEVINL float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// explicit global-state-space accesses for pointers that arrive as void* kernel parameters (generic LD/ST/ATOM
+// otherwise: the compiler cannot prove the address space)
+MDT_DEVINL uint64_t gaddr(const void* p) { return static_cast<uint64_t>(__cvta_generic_to_global(p)); }
+MDT_DEVINL void stg128(uint64_t a, float4 v) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+MDT_DEVINL void stg64(uint64_t a, uint2 v) {
+  asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(a), "r"(v.x), "r"(v.y) : "memory");
+}
+MDT_DEVINL float4 ldg128(uint64_t a) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a) : "memory");
+  return v;
+}
+MDT_DEVINL float4 ldg128_nc(uint64_t a) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a));
+  return v;
+}
+MDT_DEVINL uint2 ldg64_nc(uint64_t a) {
+  uint2 v;
+  asm volatile("ld.global.nc.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(a));
+  return v;
+}
+MDT_DEVINL void red_add_v4(uint64_t a, float4 v) {  // one 16-byte fp32 reduction (REDG.E.ADD.F32x4)
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

@@ -111,62 +111,55 @@ MDT_DEVINL uint2 pack4_bf16(float4 v) { return make_uint2(pack_bf16(v.x, v.y), p
 MDT_DEVINL float4 unpack4_bf16(uint2 u) { return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y)); }
 
 template <int EPI>
-MDT_DEVINL void epilogue_chunk(const GemmParams& p, const float* stg, int row_base, int nrows, int col, int lane) {
+MDT_DEVINL void epilogue_chunk(const GemmParams& p, uint32_t stg, int row_base, int nrows, int col, int lane) {
   const int rsub = lane >> 3, c4 = (lane & 7) * 4;
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (EPI != EPI_ATOMIC && p.bias) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
+  if (EPI != EPI_ATOMIC && p.bias) bias4 = ldg128_nc(gaddr(p.bias + col));
   const size_t row0 = static_cast<size_t>(row_base + rsub);
-  size_t o_out = row0 * p.ldo + col;
-  size_t o_aux = row0 * p.ld_aux + col;
-  size_t o_res = row0 * p.ld_resid + col;
-  const float* sp = stg + rsub * kStgStride + c4;
+  const int osz = (EPI == EPI_ATOMIC || EPI == EPI_GATE_RESID || (EPI == EPI_STORE && p.out_fp32)) ? 4 : 2;
+  uint64_t a_out = gaddr(p.out) + (row0 * p.ldo + col) * osz;
+  uint64_t a_aux = gaddr(p.aux) + (row0 * p.ld_aux + col) * 2;
+  uint64_t a_res = gaddr(p.resid) + (row0 * p.ld_resid + col) * 4;
+  const uint64_t s_out = 4ull * p.ldo * osz, s_aux = 8ull * p.ld_aux, s_res = 16ull * p.ld_resid;
+  uint32_t sp = stg + (rsub * kStgStride + c4) * 4;
 #pragma unroll
-  for (int i = 0; i < 8; ++i, o_out += 4 * static_cast<size_t>(p.ldo), o_aux += 4 * static_cast<size_t>(p.ld_aux),
-           o_res += 4 * static_cast<size_t>(p.ld_resid), sp += 4 * kStgStride) {
+  for (int i = 0; i < 8; ++i, a_out += s_out, a_aux += s_aux, a_res += s_res, sp += 4 * kStgStride * 4) {
     if (4 * i + rsub >= nrows) break;
-    float4 v = *reinterpret_cast<const float4*>(sp);
+    float4 v = lds128(sp);
     if constexpr (EPI == EPI_ATOMIC) {
-      float* o = reinterpret_cast<float*>(p.out) + o_out;
-      atomicAdd(o + 0, v.x), atomicAdd(o + 1, v.y), atomicAdd(o + 2, v.z), atomicAdd(o + 3, v.w);
+      red_add_v4(a_out, v);
     } else {
       v.x += bias4.x, v.y += bias4.y, v.z += bias4.z, v.w += bias4.w;
       if constexpr (EPI == EPI_STORE) {
         if (p.resid) {
-          const float4 r = *reinterpret_cast<const float4*>(p.resid + o_res);
+          const float4 r = ldg128(a_res);
           v.x += r.x, v.y += r.y, v.z += r.z, v.w += r.w;
         }
         if (p.act == ACT_SILU) v = make_float4(silu(v.x), silu(v.y), silu(v.z), silu(v.w));
-        if (p.out_fp32)
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o_out) = v;
-        else
-          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o_out) = pack4_bf16(v);
+        if (p.out_fp32) stg128(a_out, v); else stg64(a_out, pack4_bf16(v));
       } else if constexpr (EPI == EPI_GELU) {
         // pre-activation is rounded to bf16 first (as a bf16 nn.Linear output would be), GELU on the rounded value
         const uint2 pre = pack4_bf16(v);
-        if (p.aux) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.aux) + o_aux) = pre;
+        if (p.aux) stg64(a_aux, pre);
         const float4 h = unpack4_bf16(pre);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o_out) =
-            pack4_bf16(make_float4(gelu_tanh(h.x), gelu_tanh(h.y), gelu_tanh(h.z), gelu_tanh(h.w)));
+        stg64(a_out, pack4_bf16(make_float4(gelu_tanh(h.x), gelu_tanh(h.y), gelu_tanh(h.z), gelu_tanh(h.w))));
       } else if constexpr (EPI == EPI_GATE_RESID) {
-        if (p.aux) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.aux) + o_aux) = pack4_bf16(v);
+        if (p.aux) stg64(a_aux, pack4_bf16(v));
         const size_t b = (row0 + 4 * i) / p.rows_per_group;
-        const float4 g = *reinterpret_cast<const float4*>(p.gate + b * p.ld_gate + col);
-        const float4 r = *reinterpret_cast<const float4*>(p.resid + o_res);
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o_out) =
-            make_float4(fmaf(g.x, v.x, r.x), fmaf(g.y, v.y, r.y), fmaf(g.z, v.z, r.z), fmaf(g.w, v.w, r.w));
+        const float4 g = ldg128_nc(gaddr(p.gate + b * p.ld_gate + col));
+        const float4 r = ldg128(a_res);  // may alias `out` (in-place residual update): plain load, read-before-write
+        stg128(a_out, make_float4(fmaf(g.x, v.x, r.x), fmaf(g.y, v.y, r.y), fmaf(g.z, v.z, r.z), fmaf(g.w, v.w, r.w)));
       } else if constexpr (EPI == EPI_DGELU) {
-        const float4 h = unpack4_bf16(
-            *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + o_aux));
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o_out) =
-            pack4_bf16(make_float4(v.x * gelu_tanh_grad(h.x), v.y * gelu_tanh_grad(h.y), v.z * gelu_tanh_grad(h.z),
-                                   v.w * gelu_tanh_grad(h.w)));
+        const float4 h = unpack4_bf16(ldg64_nc(a_aux));
+        stg64(a_out, pack4_bf16(make_float4(v.x * gelu_tanh_grad(h.x), v.y * gelu_tanh_grad(h.y),
+                                            v.z * gelu_tanh_grad(h.z), v.w * gelu_tanh_grad(h.w))));
       }
     }
   }
 }
 
 // ragged right edge (N % 4 != 0 inside this 4-column group): element-wise, same arithmetic, cold path
-__device__ __noinline__ void epilogue_ragged(const GemmParams& p, const float* stg, int row_base, int nrows, int col,
+__device__ __noinline__ void epilogue_ragged(const GemmParams& p, uint32_t stg, int row_base, int nrows, int col,
                                              int lane) {
   const int rsub = lane >> 3, c4 = (lane & 7) * 4;
   for (int i = 0; i < 8; ++i) {
@@ -174,7 +167,7 @@ __device__ __noinline__ void epilogue_ragged(const GemmParams& p, const float* s
     if (rr >= nrows) break;
     const size_t row = static_cast<size_t>(row_base + rr);
     for (int j = 0; j < 4 && col + j < p.N; ++j) {
-      float v = stg[rr * kStgStride + c4 + j];
+      float v = lds32(stg + (rr * kStgStride + c4 + j) * 4);
       const int c = col + j;
       if (p.epi == EPI_ATOMIC) {
         atomicAdd(reinterpret_cast<float*>(p.out) + row * p.ldo + c, v);
@@ -345,7 +338,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int row_base = m0 + lane_group * 32;
       int nrows = p.M - row_base;
       nrows = nrows > 32 ? 32 : nrows;
-      float* stg = staging + ew * kStgFloats;
+      const uint32_t stg = smem_u32(staging) + ew * kStgFloats * 4;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * BLOCK_N +
                              col_half * kColsPerWarp;
 #pragma unroll 1
@@ -355,11 +348,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tcgen05_wait_ld();
         const int col0 = n0 + col_half * kColsPerWarp + c;
         if (nrows > 0 && col0 < p.N) {  // warp-uniform
-          float4* dst = reinterpret_cast<float4*>(stg + lane * kStgStride);
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                 __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            sts128(stg + (lane * kStgStride + 4 * q) * 4, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
           __syncwarp();
           const int col = col0 + (lane & 7) * 4;
           if (col + 4 <= p.N) {

@@ -13,9 +13,10 @@
 // [N,K]); "MN-major" = the M/N index contiguous (used by dgrad: B = W[N,K] read as [K_out, N_contract]; and by
 // wgrad: both operands are token-major [tokens, features] with the contraction over tokens).
 //
-// Scheduling: tile mode (each CTA takes whole output tiles, strided) for forward/dgrad, and stream-K mode
-// (the (tile, k-block) iteration space is cut into equal contiguous ranges, partial tiles reduced with fp32
-// red.global.add) for wgrad / small-output GEMMs whose tile count does not fill 148 SMs.
+// Scheduling: persistent tile loop (each CTA group takes whole output tiles, strided) for forward/dgrad; for the
+// accumulate epilogue (wgrad, long-K small-output GEMMs) the K range is additionally cut into slices so that
+// tiles x slices fills the machine, units are walked slice-major and partial tiles are reduced with fp32
+// red.global.add.v4 in the (pipelined) epilogue.
 //
 // Reference ops this replaces: every nn.Linear of models/maskdit.py (timm Attention.qkv/proj, Mlp.fc1/fc2,
 // adaLN_modulation, DecoderLayer.linear, TimestepEmbedder.mlp, LabelEmbedder) and their autograd backward.
@@ -53,43 +54,31 @@ struct GemmCfg {
 };
 
 struct UnitSched {
-  // Iterates the work units of this CTA; identical sequence in every warp role.
-  int mode, num_kb, num_tiles, num_n_tiles;
-  long long it, it_end;  // stream-K: global iteration range
-  int tile, grid;        // tile mode
+  // Iterates the work units of this CTA group; identical sequence in every warp role (and in both CTAs of a pair).
+  // Units are (k-slice, tile) pairs in SLICE-major order, dealt round-robin to the groups: at any moment the resident
+  // groups work on the same k-slice of different tiles, so A/B panels are shared through L2 exactly as in a plain
+  // tiled GEMM (a tile-major stream-K order made the wgrad GEMMs DRAM-bound: every unit streamed private panels).
+  // splits == 1 is the ordinary persistent tile loop.
+  int num_kb, num_tiles, num_n_tiles, splits, grid;
+  int unit, num_units;
   int cur_tile, kb0, kb1;
   MDT_DEVINL void init(const GemmParams& p, int cg) {
-    mode = p.streamk;
     num_kb = p.num_kb;
     num_n_tiles = p.num_n_tiles;
     num_tiles = p.num_m_tiles * p.num_n_tiles;
-    grid = gridDim.x / cg;              // CTA groups; both CTAs of a pair walk the same unit sequence
-    const int gid = blockIdx.x / cg;
-    if (mode) {
-      long long total = static_cast<long long>(num_tiles) * num_kb;
-      it = total * gid / grid;
-      it_end = total * (gid + 1) / grid;
-    } else {
-      tile = gid;
-    }
+    splits = p.streamk;  // number of k-slices (>= 1)
+    num_units = num_tiles * splits;
+    grid = gridDim.x / cg;
+    unit = blockIdx.x / cg;
   }
   MDT_DEVINL bool next() {
-    if (mode) {
-      if (it >= it_end) return false;
-      cur_tile = static_cast<int>(it / num_kb);
-      kb0 = static_cast<int>(it % num_kb);
-      long long rem = it_end - it;
-      kb1 = (num_kb - kb0 < rem) ? num_kb : kb0 + static_cast<int>(rem);
-      it += kb1 - kb0;
-      return true;
-    } else {
-      if (tile >= num_tiles) return false;
-      cur_tile = tile;
-      kb0 = 0;
-      kb1 = num_kb;
-      tile += grid;
-      return true;
-    }
+    if (unit >= num_units) return false;
+    const int slice = unit / num_tiles;
+    cur_tile = unit - slice * num_tiles;
+    kb0 = static_cast<int>(static_cast<long long>(num_kb) * slice / splits);
+    kb1 = static_cast<int>(static_cast<long long>(num_kb) * (slice + 1) / splits);
+    unit += grid;
+    return true;
   }
   MDT_DEVINL int m_tile() const { return cur_tile / num_n_tiles; }
   MDT_DEVINL int n_tile() const { return cur_tile % num_n_tiles; }
@@ -341,17 +330,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t stg = smem_u32(staging) + ew * kStgFloats * 4;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * BLOCK_N +
                              col_half * kColsPerWarp;
-#pragma unroll 1
-      for (int c = 0; c < kColsPerWarp; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c, r);
+      // TMEM -> registers is double buffered: the load of chunk c+1 is in flight while chunk c is transposed/stored
+      uint32_t r[2][32];
+      tmem_ld_32x32b_x32(taddr, r[0]);
+#pragma unroll
+      for (int ci = 0; ci < kColsPerWarp / 32; ++ci) {
+        const int c = ci * 32;
         tcgen05_wait_ld();
+        if (ci + 1 < kColsPerWarp / 32) tmem_ld_32x32b_x32(taddr + c + 32, r[(ci + 1) & 1]);
+        const uint32_t* rc = r[ci & 1];
         const int col0 = n0 + col_half * kColsPerWarp + c;
         if (nrows > 0 && col0 < p.N) {  // warp-uniform
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            sts128(stg + (lane * kStgStride + 4 * q) * 4, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            sts128(stg + (lane * kStgStride + 4 * q) * 4, __uint_as_float(rc[4 * q]), __uint_as_float(rc[4 * q + 1]),
+                   __uint_as_float(rc[4 * q + 2]), __uint_as_float(rc[4 * q + 3]));
           __syncwarp();
           const int col = col0 + (lane & 7) * 4;
           if (col + 4 <= p.N) {
@@ -460,9 +453,22 @@ static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
   p.gate = a.gate, p.ld_gate = a.ld_gate, p.rows_per_group = a.rows_per_group > 0 ? a.rows_per_group : 1;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int groups = num_sms() / CG;  // CTA groups resident at once (1 CTA per SM)
-  // stream-K whenever the epilogue is a pure fp32 accumulation
-  p.streamk = (a.epi == EPI_ATOMIC) ? 1 : 0;
-  long long units = p.streamk ? static_cast<long long>(tiles) * p.num_kb : tiles;
+  // k-slices: only for the accumulate epilogue (fp32 red.add).  Pick the smallest slice count whose unit count
+  // fills >= 90 % of the last wave; each extra slice costs one more tile-sized pass of L2 reductions.
+  int splits = 1;
+  if (a.epi == EPI_ATOMIC) {
+    double best_eff = 0.0;
+    const int cand[9] = {1, 2, 3, 4, 6, 8, 12, 16, 32};
+    for (int c : cand) {
+      if (c > p.num_kb) break;
+      const long long u = static_cast<long long>(tiles) * c;
+      const double eff = static_cast<double>(u) / (static_cast<double>((u + groups - 1) / groups) * groups);
+      if (eff > best_eff + 0.03) best_eff = eff, splits = c;
+      if (eff >= 0.9) break;
+    }
+  }
+  p.streamk = splits;
+  const long long units = static_cast<long long>(tiles) * splits;
   const int grid = static_cast<int>(units < groups ? units : groups) * CG;
   if (grid <= 0) return MDT_OK;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, CG>;
@@ -496,16 +502,12 @@ static int dispatch_n(const mdt_gemm_args& a, cudaStream_t stream) {
   // SM pairs (256-row tiles) whenever there are at least two 128-row panels; single CTAs for skinny problems
   int cg = (a.M > BLOCK_M) ? 2 : 1;
   if (g_force_cg == 1 || g_force_cg == 2) cg = g_force_cg;
-  // pick the tile width that wastes the fewest columns; ties -> wider tile.  With an MN-major B operand a CTA of a
-  // pair stages BLOCK_N/2 columns as 64-wide TMA boxes, so 192 is not available there.
+  // Tile width: 256 columns unless the problem is narrower.  Measured on B200 (tools/probe_gemm3.py): for N = 1152
+  // a 256-wide tile (5 tiles, 10 % padding) beats 192 (no padding) and 128 by 1.2-1.3x, because the epilogue and
+  // the per-tile pipeline fill are amortised over twice the MMA work.
   int best = 256;
-  long long best_cost = -1;
-  const int cands[3] = {256, 192, 128};
-  for (int c : cands) {
-    if (cg == 2 && B_MN && c == 192) continue;
-    long long cost = static_cast<long long>((a.N + c - 1) / c) * c;
-    if (best_cost < 0 || cost < best_cost) best = c, best_cost = cost;
-  }
+  if (a.N <= 128) best = 128;
+  else if (a.N <= 192 && !(cg == 2 && B_MN)) best = 192;
   if (a.block_n == 128 || a.block_n == 192 || a.block_n == 256) best = a.block_n;
   if (cg == 2 && B_MN && best == 192) best = 128;
   if (cg == 2) {

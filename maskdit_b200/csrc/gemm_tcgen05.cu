@@ -188,6 +188,32 @@ __device__ __noinline__ void epilogue_ragged(const GemmParams& p, uint32_t stg, 
   }
 }
 
+// One warp's share of a tile (32 rows x kChunks*32 columns) for ONE epilogue kind.  The chunk loop is deliberately
+// rolled and single-buffered: unrolling / prefetching the next tcgen05.ld was measured SLOWER on B200 (12.3k vs 8.8k
+// cycles per 128x256 bf16 tile, tools/probe_gemm2.py) — the epilogue is instruction-fetch sensitive.
+template <int EPI, int kChunks>
+MDT_DEVINL void epilogue_tile(const GemmParams& p, uint32_t taddr, uint32_t stg, int row_base, int nrows, int col_base,
+                              int lane) {
+#pragma unroll 1
+  for (int ci = 0; ci < kChunks; ++ci) {
+    uint32_t rc[32];
+    tmem_ld_32x32b_x32(taddr + ci * 32, rc);
+    tcgen05_wait_ld();
+    const int col0 = col_base + ci * 32;
+    if (nrows > 0 && col0 < p.N) {  // warp-uniform
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        sts128(stg + (lane * kStgStride + 4 * q) * 4, __uint_as_float(rc[4 * q]), __uint_as_float(rc[4 * q + 1]),
+               __uint_as_float(rc[4 * q + 2]), __uint_as_float(rc[4 * q + 3]));
+      __syncwarp();
+      const int col = col0 + (lane & 7) * 4;
+      if (col + 4 <= p.N) epilogue_chunk<EPI>(p, stg, row_base, nrows, col, lane);
+      else if (col < p.N) epilogue_ragged(p, stg, row_base, nrows, col, lane);
+      __syncwarp();
+    }
+  }
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -330,37 +356,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t stg = smem_u32(staging) + ew * kStgFloats * 4;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * BLOCK_N +
                              col_half * kColsPerWarp;
-      // TMEM -> registers is double buffered: the load of chunk c+1 is in flight while chunk c is transposed/stored
-      uint32_t r[2][32];
-      tmem_ld_32x32b_x32(taddr, r[0]);
-#pragma unroll
-      for (int ci = 0; ci < kColsPerWarp / 32; ++ci) {
-        const int c = ci * 32;
-        tcgen05_wait_ld();
-        if (ci + 1 < kColsPerWarp / 32) tmem_ld_32x32b_x32(taddr + c + 32, r[(ci + 1) & 1]);
-        const uint32_t* rc = r[ci & 1];
-        const int col0 = n0 + col_half * kColsPerWarp + c;
-        if (nrows > 0 && col0 < p.N) {  // warp-uniform
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            sts128(stg + (lane * kStgStride + 4 * q) * 4, __uint_as_float(rc[4 * q]), __uint_as_float(rc[4 * q + 1]),
-                   __uint_as_float(rc[4 * q + 2]), __uint_as_float(rc[4 * q + 3]));
-          __syncwarp();
-          const int col = col0 + (lane & 7) * 4;
-          if (col + 4 <= p.N) {
-            switch (p.epi) {
-              case EPI_STORE: epilogue_chunk<EPI_STORE>(p, stg, row_base, nrows, col, lane); break;
-              case EPI_GELU: epilogue_chunk<EPI_GELU>(p, stg, row_base, nrows, col, lane); break;
-              case EPI_GATE_RESID: epilogue_chunk<EPI_GATE_RESID>(p, stg, row_base, nrows, col, lane); break;
-              case EPI_DGELU: epilogue_chunk<EPI_DGELU>(p, stg, row_base, nrows, col, lane); break;
-              case EPI_ATOMIC: epilogue_chunk<EPI_ATOMIC>(p, stg, row_base, nrows, col, lane); break;
-              default: break;
-            }
-          } else if (col < p.N) {
-            epilogue_ragged(p, stg, row_base, nrows, col, lane);
-          }
-          __syncwarp();
-        }
+      const int col_base = n0 + col_half * kColsPerWarp;
+      constexpr int kChunks = kColsPerWarp / 32;
+      switch (p.epi) {  // one switch per tile: a launch only ever executes the instructions of its own epilogue
+        case EPI_STORE: epilogue_tile<EPI_STORE, kChunks>(p, taddr, stg, row_base, nrows, col_base, lane); break;
+        case EPI_GELU: epilogue_tile<EPI_GELU, kChunks>(p, taddr, stg, row_base, nrows, col_base, lane); break;
+        case EPI_GATE_RESID: epilogue_tile<EPI_GATE_RESID, kChunks>(p, taddr, stg, row_base, nrows, col_base, lane); break;
+        case EPI_DGELU: epilogue_tile<EPI_DGELU, kChunks>(p, taddr, stg, row_base, nrows, col_base, lane); break;
+        case EPI_ATOMIC: epilogue_tile<EPI_ATOMIC, kChunks>(p, taddr, stg, row_base, nrows, col_base, lane); break;
+        default: epilogue_tile<99, kChunks>(p, taddr, stg, row_base, nrows, col_base, lane); break;  // debug: no stores
       }
       tcgen05_fence_before();
       __syncwarp();

@@ -11,6 +11,8 @@
 //
 // Backward = two kernels with no atomics: dQ (block = 64 queries, loops over keys; also emits delta = rowsum(dO*O))
 // and dK/dV (block = 64 keys, loops over queries, transposed formulation S^T = K Q^T).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/maskdit_b200.h"
 
@@ -354,7 +356,23 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 
 }  // namespace mdt
 
+namespace mdt {
+// tcgen05 kernels (attention_tc.cu); MDT_ERR_UNSUPPORTED = shape outside their range -> mma.sync kernels below
+int attention_tc_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale, cudaStream_t st);
+int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int T,
+                     int H, int dh, float scale, cudaStream_t st);
+}  // namespace mdt
+
 using namespace mdt;
+
+static bool use_tc() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MDT_ATTN_TC");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 static int dp_of(int dh) {
   if (dh % 8) return 0;
@@ -381,6 +399,10 @@ int mdt_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int 
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return MDT_ERR_ARG;
   dim3 grid((T + kTile - 1) / kTile, B * H);
   const float scale = 1.f / sqrtf(static_cast<float>(dh));
+  if (use_tc()) {
+    const int rc = attention_tc_fwd(qkv, out, lse, B, T, H, dh, scale, static_cast<cudaStream_t>(stream));
+    if (rc != MDT_ERR_UNSUPPORTED) return rc;
+  }
   MDT_DP_DISPATCH(dp, attn_fwd_kernel<kDP><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
                           static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, T, H, dh,
                           scale));
@@ -397,6 +419,10 @@ int mdt_attention_bwd(const void* qkv, const void* out, const void* dout, const 
   const float scale = 1.f / sqrtf(static_cast<float>(dh));
   float* delta = const_cast<float*>(lse) + static_cast<size_t>(B) * H * T;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (use_tc()) {
+    const int rc = attention_tc_bwd(qkv, out, dout, lse, dqkv, B, T, H, dh, scale, st);
+    if (rc != MDT_ERR_UNSUPPORTED) return rc;
+  }
   MDT_DP_DISPATCH(dp, {
     attn_bwd_dq_kernel<kDP><<<grid, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv),
                                                   static_cast<const __nv_bfloat16*>(out),

@@ -1,0 +1,443 @@
+// Attention core on the 5th-gen tensor cores (tcgen05.mma, S / dP / O / dQ / dK / dV accumulators in TMEM) for the
+// MaskDiT training shapes: T = 128 or 256 tokens per sample, head_dim 72 (encoder, zero-padded to 80) or 32 (decoder).
+// Replaces softmax(q k^T / sqrt(dh)) v of timm Attention (reference ctor site models/maskdit.py:178) and its backward.
+//
+//   forward : CTA = (128 queries of one (b,h)); S = Q K^T -> TMEM; one thread per query row does the softmax straight
+//             out of TMEM (two passes, fp32), writes P (bf16) to smem; O = P V -> TMEM -> bf16 rows + log-sum-exp.
+//   backward: CTA = one (b,h); per (query block, key block): S = Q K^T and dP = dO V^T -> TMEM; row threads form
+//             P = exp(S - lse), dS = P (dP - delta) scale -> smem (bf16); dV += P^T dO, dK += dS^T Q, dQ += dS K
+//             accumulate in TMEM over the loop.  No atomics, no recompute pass, deterministic.
+//
+// Shared-memory operand tiles use the UMMA canonical NO-SWIZZLE layout: 8x8 "core matrices" of 128 contiguous bytes
+// (8 rows of 16 B).  A token-major tile [rows x DP] is stored as  off(row, c8) = (row/8)*ROWBLK + c8*128 + (row%8)*16
+// with ROWBLK = (DP/8)*128.  The SAME bytes serve as a K-major operand (contraction over head_dim: LBO = 128,
+// SBO = ROWBLK) and as an MN-major operand (contraction over tokens: SBO = 128, LBO = ROWBLK), so Q, K, V, dO, P and dS
+// are each staged exactly once.  head_dim 72 -> 9 real 16-byte chunks + 1 zero chunk per row (144-byte rows cannot
+// be TMA-swizzled; the tiles are filled with coalesced 16-byte loads instead).
+#include "common.cuh"
+#include "../../include/maskdit_b200.h"
+
+namespace mdt {
+
+constexpr int kQB = 128;  // query rows per MMA (TMEM lanes) == threads per CTA
+
+MDT_DEVINL uint64_t make_smem_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fffu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= 1ull << 46;  // version = 1 (Blackwell); layout type 0 = SWIZZLE_NONE
+  return d;
+}
+MDT_DEVINL void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+MDT_DEVINL void sts128u(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+MDT_DEVINL uint4 ldg128u_nc(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(gaddr(p)));
+  return v;
+}
+
+template <int DP>
+struct TokTile {
+  static constexpr int CH = DP / 8;          // 16-byte chunks per row
+  static constexpr int ROWBLK = CH * 128;    // bytes per 8-row block
+  static constexpr int CG4 = (CH + 3) / 4;   // chunk groups of 4
+  MDT_DEVINL static uint32_t off(int row, int c8) { return (row >> 3) * ROWBLK + c8 * 128 + (row & 7) * 16; }
+  // global [rows, dh] (row stride gstride elements) -> smem tile; warp item = 8 rows x 4 chunks (64 B per row from
+  // global = 2 full sectors; 128 B contiguous per quarter-warp into smem = conflict free)
+  MDT_DEVINL static void load(uint32_t s_base, const __nv_bfloat16* g, long long gstride, int rows, int dh) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = lane & 7, cl = lane >> 3;
+    const int items = (rows >> 3) * CG4;
+    for (int it = warp; it < items; it += kQB / 32) {
+      const int rb = it / CG4, cg = it - rb * CG4;
+      const int c8 = cg * 4 + cl, row = rb * 8 + r;
+      if (c8 < CH) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (c8 * 8 < dh) v = ldg128u_nc(g + row * gstride + c8 * 8);
+        sts128u(s_base + off(row, c8), v);
+      }
+    }
+  }
+};
+
+// C[128 x N] (+)= A[128 x K] * B[N x K]^T, K-major views of token tiles; K = DP
+template <int DP>
+MDT_DEVINL void mma_kk(uint32_t tmem_d, uint32_t sa, uint32_t sb, int n, bool acc0) {
+  constexpr uint32_t RB = TokTile<DP>::ROWBLK;
+  const uint32_t idesc = make_idesc_bf16(kQB, n, 0, 0);
+#pragma unroll
+  for (int k = 0; k < DP / 16; ++k)
+    umma_bf16(tmem_d, make_smem_desc_nosw(sa + k * 256, 128, RB), make_smem_desc_nosw(sb + k * 256, 128, RB), idesc,
+              (acc0 || k > 0) ? 1u : 0u);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+template <int DP, int TK>
+__global__ void __launch_bounds__(kQB)
+attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
+                   int T, int H, int dh, float scale) {
+  using TT = TokTile<DP>;
+  constexpr int kPBlk = (TK / 8) * 128;                       // bytes per 8-query block of P
+  constexpr int kTmemCols = (TK + DP <= 256) ? 256 : 512;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sQ = smem_u32(smem), sK = sQ + kQB * DP * 2, sV = sK + TK * DP * 2, sP = sV + TK * DP * 2;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (kQB + 2 * TK) * DP * 2 + kQB * TK * 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.y / H, h = blockIdx.y % H, q0 = blockIdx.x * kQB;
+  const long long rs = 3LL * H * dh;
+  const __nv_bfloat16* base = qkv + static_cast<long long>(b) * T * rs;
+  if (warp == 0) tmem_alloc<kTmemCols>(tmem_slot);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  TT::load(sQ, base + q0 * rs + h * dh, rs, kQB, dh);
+  TT::load(sK, base + (H + h) * dh, rs, TK, dh);
+  TT::load(sV, base + (2 * H + h) * dh, rs, TK, dh);
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tO = tmem + TK;
+  if (tid == 0) {
+    mma_kk<DP>(tS, sQ, sK, TK, false);
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tcgen05_fence_after();
+
+  // softmax of this thread's row, straight out of TMEM (lane = row)
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  const float sl = scale * 1.4426950408889634f;
+  float m = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < TK; c += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(tS + lane_addr + c, r);
+    tcgen05_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+  }
+  const float msl = m * sl;
+  float l = 0.f;
+  const uint32_t prow = sP + (tid >> 3) * kPBlk + (tid & 7) * 16;
+#pragma unroll 1
+  for (int c = 0; c < TK; c += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(tS + lane_addr + c, r);
+    tcgen05_wait_ld();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float p[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        p[j] = exp2f(__uint_as_float(r[8 * g + j]) * sl - msl);
+        l += p[j];
+      }
+      sts128u(prow + (c / 8 + g) * 128,
+              make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7])));
+    }
+  }
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tcgen05_fence_after();
+    // O[128 x DP] = P[128 x TK] (K-major) * V (MN-major: N = head dim, K = keys)
+    const uint32_t idesc = make_idesc_bf16(kQB, DP, 0, 1);
+#pragma unroll 4
+    for (int k = 0; k < TK / 16; ++k)
+      umma_bf16(tO, make_smem_desc_nosw(sP + k * 256, 128, kPBlk),
+                make_smem_desc_nosw(sV + k * 2 * TT::ROWBLK, TT::ROWBLK, 128), idesc, k > 0 ? 1u : 0u);
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 1);
+  tcgen05_fence_after();
+  const float inv_l = 1.f / l;
+  const int q = q0 + tid;
+  __nv_bfloat16* orow = out + (static_cast<long long>(b) * T + q) * (H * dh) + h * dh;
+#pragma unroll
+  for (int c = 0; c < DP; c += 16) {
+    uint32_t r[16];
+    tmem_ld_32x32b_x16(tO + lane_addr + c, r);
+    tcgen05_wait_ld();
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      if (c + 8 * g < dh) {
+        const uint4 v = make_uint4(
+            pack_bf16(__uint_as_float(r[8 * g + 0]) * inv_l, __uint_as_float(r[8 * g + 1]) * inv_l),
+            pack_bf16(__uint_as_float(r[8 * g + 2]) * inv_l, __uint_as_float(r[8 * g + 3]) * inv_l),
+            pack_bf16(__uint_as_float(r[8 * g + 4]) * inv_l, __uint_as_float(r[8 * g + 5]) * inv_l),
+            pack_bf16(__uint_as_float(r[8 * g + 6]) * inv_l, __uint_as_float(r[8 * g + 7]) * inv_l));
+        *reinterpret_cast<uint4*>(orow + c + 8 * g) = v;
+      }
+    }
+  }
+  if (lse) lse[(static_cast<long long>(b) * H + h) * T + q] = m * scale + logf(l);
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc<kTmemCols>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward (one CTA per (b,h); NB = T / 128 query blocks == key blocks)
+// ------------------------------------------------------------------------------------------------------------
+template <int DP, int NB>
+__global__ void __launch_bounds__(kQB)
+attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
+                   const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
+                   __nv_bfloat16* __restrict__ dqkv, int H, int dh, float scale) {
+  using TT = TokTile<DP>;
+  constexpr int T = NB * kQB;
+  constexpr int kPBlk = (kQB / 8) * 128;  // P / dS tiles are [128 queries x 128 keys]
+  constexpr int kTileBytes = T * DP * 2;
+  static_assert(256 + DP + 2 * NB * DP <= 512, "TMEM budget");
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sQ = smem_u32(smem), sK = sQ + kTileBytes, sV = sK + kTileBytes, sdO = sV + kTileBytes;
+  const uint32_t sP = sdO + kTileBytes, sdS = sP + kQB * kQB * 2;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 4 * kTileBytes + 2 * kQB * kQB * 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const long long rs = 3LL * H * dh;
+  const int HD = H * dh;
+  const __nv_bfloat16* base = qkv + static_cast<long long>(b) * T * rs;
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  TT::load(sQ, base + h * dh, rs, T, dh);
+  TT::load(sK, base + (H + h) * dh, rs, T, dh);
+  TT::load(sV, base + (2 * H + h) * dh, rs, T, dh);
+  TT::load(sdO, dout + static_cast<long long>(b) * T * HD + h * dh, HD, T, dh);
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256, tKV = tmem + 256 + DP;  // dK[j] | dV[j] at tKV + j*2DP
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  const float sl = scale * 1.4426950408889634f;
+  constexpr uint32_t RB = TT::ROWBLK;
+  constexpr uint32_t kBlkBytes = 16 * RB;  // 128 token rows
+  uint32_t phase = 0;
+
+  if (tid == 0) {  // first S / dP
+    mma_kk<DP>(tS, sQ, sK, kQB, false);
+    mma_kk<DP>(tdP, sdO, sV, kQB, false);
+    umma_commit(bar);
+  }
+  for (int qb = 0; qb < NB; ++qb) {
+    const int q = qb * kQB + tid;
+    // delta = rowsum(dO * O), lse of this query row
+    float delta = 0.f;
+    {
+      const __nv_bfloat16* orow = out + (static_cast<long long>(b) * T + q) * HD + h * dh;
+      const __nv_bfloat16* drow = dout + (static_cast<long long>(b) * T + q) * HD + h * dh;
+      for (int c = 0; c < dh; c += 8) {
+        const uint4 a = ldg128u_nc(orow + c), d = ldg128u_nc(drow + c);
+        delta += bf16_lo(a.x) * bf16_lo(d.x) + bf16_hi(a.x) * bf16_hi(d.x) + bf16_lo(a.y) * bf16_lo(d.y) +
+                 bf16_hi(a.y) * bf16_hi(d.y) + bf16_lo(a.z) * bf16_lo(d.z) + bf16_hi(a.z) * bf16_hi(d.z) +
+                 bf16_lo(a.w) * bf16_lo(d.w) + bf16_hi(a.w) * bf16_hi(d.w);
+      }
+    }
+    const float lsl = lse[(static_cast<long long>(b) * H + h) * T + q] * 1.4426950408889634f;
+    for (int kb = 0; kb < NB; ++kb) {
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      tcgen05_fence_after();
+      const uint32_t prow = (tid >> 3) * kPBlk + (tid & 7) * 16;
+#pragma unroll 1
+      for (int c = 0; c < kQB; c += 32) {
+        uint32_t rs_[32], rp[32];
+        tmem_ld_32x32b_x32(tS + lane_addr + c, rs_);
+        tmem_ld_32x32b_x32(tdP + lane_addr + c, rp);
+        tcgen05_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float p[8], ds[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            p[j] = exp2f(__uint_as_float(rs_[8 * g + j]) * sl - lsl);
+            ds[j] = p[j] * (__uint_as_float(rp[8 * g + j]) - delta) * scale;
+          }
+          const uint32_t o = prow + (c / 8 + g) * 128;
+          sts128u(sP + o, make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]),
+                                     pack_bf16(p[6], p[7])));
+          sts128u(sdS + o, make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]),
+                                      pack_bf16(ds[6], ds[7])));
+        }
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tcgen05_fence_after();
+        const uint32_t tdK = tKV + kb * 2 * DP, tdV = tdK + DP;
+        const uint32_t i_tt = make_idesc_bf16(kQB, DP, 1, 1);  // A, B both token-contracted (MN-major)
+        const uint32_t i_kt = make_idesc_bf16(kQB, DP, 0, 1);  // A K-major (keys contiguous), B token-contracted
+#pragma unroll
+        for (int k = 0; k < kQB / 16; ++k) {
+          // dV[kb] += P^T dO[qb] ; dK[kb] += dS^T Q[qb]   (contraction over the 128 queries)
+          const uint64_t aP = make_smem_desc_nosw(sP + k * 2 * kPBlk, kPBlk, 128);
+          const uint64_t aS = make_smem_desc_nosw(sdS + k * 2 * kPBlk, kPBlk, 128);
+          const uint64_t bO = make_smem_desc_nosw(sdO + qb * kBlkBytes + k * 2 * RB, RB, 128);
+          const uint64_t bQ = make_smem_desc_nosw(sQ + qb * kBlkBytes + k * 2 * RB, RB, 128);
+          umma_bf16(tdV, aP, bO, i_tt, (qb > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tdK, aS, bQ, i_tt, (qb > 0 || k > 0) ? 1u : 0u);
+          // dQ[qb] += dS K[kb]   (contraction over the 128 keys)
+          const uint64_t aS2 = make_smem_desc_nosw(sdS + k * 256, 128, kPBlk);
+          const uint64_t bK = make_smem_desc_nosw(sK + kb * kBlkBytes + k * 2 * RB, RB, 128);
+          umma_bf16(tdQ, aS2, bK, i_kt, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        // next (qb, kb): S and dP can be issued right away, one commit covers everything issued so far
+        int nq = qb, nk = kb + 1;
+        if (nk == NB) nk = 0, ++nq;
+        if (nq < NB) {
+          mma_kk<DP>(tS, sQ + nq * kBlkBytes, sK + nk * kBlkBytes, kQB, false);
+          mma_kk<DP>(tdP, sdO + nq * kBlkBytes, sV + nk * kBlkBytes, kQB, false);
+        }
+        umma_commit(bar);
+      }
+    }
+    // dQ of this query block is complete once the last commit lands; the same commit also covers the next S/dP
+    mbar_wait(bar, phase);
+    tcgen05_fence_after();
+    __nv_bfloat16* grow = dqkv + (static_cast<long long>(b) * T + q) * rs + h * dh;
+#pragma unroll
+    for (int c = 0; c < DP; c += 16) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(tdQ + lane_addr + c, r);
+      tcgen05_wait_ld();
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        if (c + 8 * g < dh)
+          *reinterpret_cast<uint4*>(grow + c + 8 * g) = make_uint4(
+              pack_bf16(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1])),
+              pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3])),
+              pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5])),
+              pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7])));
+    }
+    // the next iteration's first wait uses the same (already completed) phase: do not flip here
+    tcgen05_fence_before();
+    __syncthreads();  // all rows read dQ before the next query block's MMAs (already queued behind this commit) reuse it
+  }
+  // dK / dV: rows = keys
+#pragma unroll 1
+  for (int kb = 0; kb < NB; ++kb) {
+    const int key = kb * kQB + tid;
+    __nv_bfloat16* krow = dqkv + (static_cast<long long>(b) * T + key) * rs + (H + h) * dh;
+    __nv_bfloat16* vrow = dqkv + (static_cast<long long>(b) * T + key) * rs + (2 * H + h) * dh;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      __nv_bfloat16* grow = which ? vrow : krow;
+      const uint32_t tacc = tKV + kb * 2 * DP + which * DP;
+#pragma unroll
+      for (int c = 0; c < DP; c += 16) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tacc + lane_addr + c, r);
+        tcgen05_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          if (c + 8 * g < dh)
+            *reinterpret_cast<uint4*>(grow + c + 8 * g) = make_uint4(
+                pack_bf16(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1])),
+                pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3])),
+                pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5])),
+                pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7])));
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host dispatch (called from attention.cu)
+// ------------------------------------------------------------------------------------------------------------
+template <int DP, int TK>
+static int launch_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale,
+                      cudaStream_t st) {
+  const int smem = (kQB + 2 * TK) * DP * 2 + kQB * TK * 2 + 64;
+  auto kern = attn_tc_fwd_kernel<DP, TK>;
+  static bool set = false;
+  if (!set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return MDT_ERR_CUDA;
+    set = true;
+  }
+  kern<<<dim3(T / kQB, B * H), kQB, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv),
+                                                 static_cast<__nv_bfloat16*>(out), lse, T, H, dh, scale);
+  return cudaGetLastError() == cudaSuccess ? MDT_OK : MDT_ERR_CUDA;
+}
+template <int DP, int NB>
+static int launch_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int H,
+                      int dh, float scale, cudaStream_t st) {
+  const int smem = 4 * NB * kQB * DP * 2 + 2 * kQB * kQB * 2 + 64;
+  auto kern = attn_tc_bwd_kernel<DP, NB>;
+  static bool set = false;
+  if (!set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return MDT_ERR_CUDA;
+    set = true;
+  }
+  kern<<<B * H, kQB, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
+                                 static_cast<const __nv_bfloat16*>(dout), lse, static_cast<__nv_bfloat16*>(dqkv), H, dh,
+                                 scale);
+  return cudaGetLastError() == cudaSuccess ? MDT_OK : MDT_ERR_CUDA;
+}
+
+// returns MDT_ERR_UNSUPPORTED when the shape is outside the tcgen05 kernels' range (caller falls back to the
+// mma.sync kernels, which handle any T / head_dim <= 80)
+int attention_tc_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale, cudaStream_t st) {
+  if (dh % 8) return MDT_ERR_UNSUPPORTED;
+  const int dp = dh <= 32 ? 32 : (dh <= 64 ? 64 : (dh <= 80 ? 80 : 0));
+  if (T == 128) {
+    if (dp == 32) return launch_fwd<32, 128>(qkv, out, lse, B, T, H, dh, scale, st);
+    if (dp == 64) return launch_fwd<64, 128>(qkv, out, lse, B, T, H, dh, scale, st);
+    if (dp == 80) return launch_fwd<80, 128>(qkv, out, lse, B, T, H, dh, scale, st);
+  } else if (T == 256) {
+    if (dp == 32) return launch_fwd<32, 256>(qkv, out, lse, B, T, H, dh, scale, st);
+    if (dp == 64) return launch_fwd<64, 256>(qkv, out, lse, B, T, H, dh, scale, st);
+    if (dp == 80) return launch_fwd<80, 256>(qkv, out, lse, B, T, H, dh, scale, st);
+  }
+  return MDT_ERR_UNSUPPORTED;
+}
+int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int T,
+                     int H, int dh, float scale, cudaStream_t st) {
+  if (dh % 8) return MDT_ERR_UNSUPPORTED;
+  const int dp = dh <= 32 ? 32 : (dh <= 64 ? 64 : (dh <= 80 ? 80 : 0));
+  if (T == 128) {
+    if (dp == 32) return launch_bwd<32, 1>(qkv, out, dout, lse, dqkv, B, H, dh, scale, st);
+    if (dp == 64) return launch_bwd<64, 1>(qkv, out, dout, lse, dqkv, B, H, dh, scale, st);
+    if (dp == 80) return launch_bwd<80, 1>(qkv, out, dout, lse, dqkv, B, H, dh, scale, st);
+  } else if (T == 256) {
+    if (dp == 32) return launch_bwd<32, 2>(qkv, out, dout, lse, dqkv, B, H, dh, scale, st);
+  }
+  return MDT_ERR_UNSUPPORTED;
+}
+
+}  // namespace mdt

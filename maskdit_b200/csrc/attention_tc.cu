@@ -38,6 +38,10 @@ MDT_DEVINL void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+MDT_DEVINL void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 MDT_DEVINL void sts128u(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -55,6 +59,9 @@ struct TokTile {
   MDT_DEVINL static uint32_t off(int row, int c8) { return (row >> 3) * ROWBLK + c8 * 128 + (row & 7) * 16; }
   // global [rows, dh] (row stride gstride elements) -> smem tile; warp item = 8 rows x 4 chunks (64 B per row from
   // global = 2 full sectors; 128 B contiguous per quarter-warp into smem = conflict free)
+  // Asynchronous (cp.async, 16 B, zero-fill for the padded chunk): every chunk of every tile is in flight at once; the
+  // caller does cp_async_wait_all() once before the first MMA.  (A register-staged fill was latency-bound: 11k of
+  // the 22k cycles a forward CTA lived.)
   MDT_DEVINL static void load(uint32_t s_base, const __nv_bfloat16* g, long long gstride, int rows, int dh) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = lane & 7, cl = lane >> 3;
@@ -63,9 +70,11 @@ struct TokTile {
       const int rb = it / CG4, cg = it - rb * CG4;
       const int c8 = cg * 4 + cl, row = rb * 8 + r;
       if (c8 < CH) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (c8 * 8 < dh) v = ldg128u_nc(g + row * gstride + c8 * 8);
-        sts128u(s_base + off(row, c8), v);
+        const bool real = c8 * 8 < dh;
+        const __nv_bfloat16* src = g + row * gstride + (real ? c8 * 8 : 0);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s_base + off(row, c8)), "l"(gaddr(src)),
+                     "r"(real ? 16 : 0)
+                     : "memory");
       }
     }
   }
@@ -91,7 +100,7 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
                    int T, int H, int dh, float scale) {
   using TT = TokTile<DP>;
   constexpr int kPBlk = (TK / 8) * 128;                       // bytes per 8-query block of P
-  constexpr int kTmemCols = (TK + DP <= 256) ? 256 : 512;
+  constexpr int kTmemCols = TK;  // O aliases S: S is dead once every row thread has written its P row to smem
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem), sK = sQ + kQB * DP * 2, sV = sK + TK * DP * 2, sP = sV + TK * DP * 2;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (kQB + 2 * TK) * DP * 2 + kQB * TK * 2);
@@ -109,12 +118,13 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
   TT::load(sQ, base + q0 * rs + h * dh, rs, kQB, dh);
   TT::load(sK, base + (H + h) * dh, rs, TK, dh);
   TT::load(sV, base + (2 * H + h) * dh, rs, TK, dh);
+  cp_async_wait_all();
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tO = tmem + TK;
+  const uint32_t tS = tmem, tO = tmem;
   if (tid == 0) {
     mma_kk<DP>(tS, sQ, sK, TK, false);
     umma_commit(bar);
@@ -231,6 +241,7 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
   TT::load(sK, base + (H + h) * dh, rs, T, dh);
   TT::load(sV, base + (2 * H + h) * dh, rs, T, dh);
   TT::load(sdO, dout + static_cast<long long>(b) * T * HD + h * dh, HD, T, dh);
+  cp_async_wait_all();
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
@@ -255,12 +266,18 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     {
       const __nv_bfloat16* orow = out + (static_cast<long long>(b) * T + q) * HD + h * dh;
       const __nv_bfloat16* drow = dout + (static_cast<long long>(b) * T + q) * HD + h * dh;
-      for (int c = 0; c < dh; c += 8) {
-        const uint4 a = ldg128u_nc(orow + c), d = ldg128u_nc(drow + c);
-        delta += bf16_lo(a.x) * bf16_lo(d.x) + bf16_hi(a.x) * bf16_hi(d.x) + bf16_lo(a.y) * bf16_lo(d.y) +
-                 bf16_hi(a.y) * bf16_hi(d.y) + bf16_lo(a.z) * bf16_lo(d.z) + bf16_hi(a.z) * bf16_hi(d.z) +
-                 bf16_lo(a.w) * bf16_lo(d.w) + bf16_hi(a.w) * bf16_hi(d.w);
+      uint4 a[DP / 8], d[DP / 8];
+#pragma unroll
+      for (int c = 0; c < DP / 8; ++c) {
+        a[c] = d[c] = make_uint4(0, 0, 0, 0);
+        if (c * 8 < dh) a[c] = ldg128u_nc(orow + c * 8), d[c] = ldg128u_nc(drow + c * 8);
       }
+#pragma unroll
+      for (int c = 0; c < DP / 8; ++c)
+        delta += bf16_lo(a[c].x) * bf16_lo(d[c].x) + bf16_hi(a[c].x) * bf16_hi(d[c].x) +
+                 bf16_lo(a[c].y) * bf16_lo(d[c].y) + bf16_hi(a[c].y) * bf16_hi(d[c].y) +
+                 bf16_lo(a[c].z) * bf16_lo(d[c].z) + bf16_hi(a[c].z) * bf16_hi(d[c].z) +
+                 bf16_lo(a[c].w) * bf16_lo(d[c].w) + bf16_hi(a[c].w) * bf16_hi(d[c].w);
     }
     const float lsl = lse[(static_cast<long long>(b) * H + h) * T + q] * 1.4426950408889634f;
     for (int kb = 0; kb < NB; ++kb) {

@@ -110,38 +110,63 @@ MDT_DEVINL void epilogue_chunk(const GemmParams& p, uint32_t stg, int row_base, 
   uint64_t a_aux = gaddr(p.aux) + (row0 * p.ld_aux + col) * 2;
   uint64_t a_res = gaddr(p.resid) + (row0 * p.ld_resid + col) * 4;
   const uint64_t s_out = 4ull * p.ldo * osz, s_aux = 8ull * p.ld_aux, s_res = 16ull * p.ld_resid;
-  uint32_t sp = stg + (rsub * kStgStride + c4) * 4;
+  const uint32_t sp = stg + (rsub * kStgStride + c4) * 4;
+  // Global operands of the epilogue are fetched for all 8 row groups BEFORE any dependent store is issued: issue is
+  // in order, so a load->store dependency inside the row loop would expose the full global latency 8 times per
+  // chunk (ncu r01: the K=1152 proj GEMM ran at 18 % tensor-pipe activity because of exactly that).
+  float4 res[8];
+  uint2 auxv[8];
+  float4 gate4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool gate_uniform = true;
+  if constexpr (EPI == EPI_GATE_RESID) {
+    const int b0 = row_base / p.rows_per_group, b1 = (row_base + nrows - 1) / p.rows_per_group;
+    gate_uniform = b0 == b1;
+    if (gate_uniform) gate4 = ldg128_nc(gaddr(p.gate + static_cast<size_t>(b0) * p.ld_gate + col));
+  }
+  if constexpr (EPI == EPI_GATE_RESID || EPI == EPI_STORE) {
+    if (EPI == EPI_GATE_RESID || p.resid) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i, a_out += s_out, a_aux += s_aux, a_res += s_res, sp += 4 * kStgStride * 4) {
+      for (int i = 0; i < 8; ++i)
+        if (4 * i + rsub < nrows) res[i] = ldg128(a_res + i * s_res);
+    }
+  }
+  if constexpr (EPI == EPI_DGELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (4 * i + rsub < nrows) auxv[i] = ldg64_nc(a_aux + i * s_aux);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
     if (4 * i + rsub >= nrows) break;
-    float4 v = lds128(sp);
+    float4 v = lds128(sp + i * (4 * kStgStride * 4));
+    const uint64_t ao = a_out + i * s_out;
     if constexpr (EPI == EPI_ATOMIC) {
-      red_add_v4(a_out, v);
+      red_add_v4(ao, v);
     } else {
       v.x += bias4.x, v.y += bias4.y, v.z += bias4.z, v.w += bias4.w;
       if constexpr (EPI == EPI_STORE) {
-        if (p.resid) {
-          const float4 r = ldg128(a_res);
-          v.x += r.x, v.y += r.y, v.z += r.z, v.w += r.w;
-        }
+        if (p.resid) v.x += res[i].x, v.y += res[i].y, v.z += res[i].z, v.w += res[i].w;
         if (p.act == ACT_SILU) v = make_float4(silu(v.x), silu(v.y), silu(v.z), silu(v.w));
-        if (p.out_fp32) stg128(a_out, v); else stg64(a_out, pack4_bf16(v));
+        if (p.out_fp32) stg128(ao, v); else stg64(ao, pack4_bf16(v));
       } else if constexpr (EPI == EPI_GELU) {
         // pre-activation is rounded to bf16 first (as a bf16 nn.Linear output would be), GELU on the rounded value
         const uint2 pre = pack4_bf16(v);
-        if (p.aux) stg64(a_aux, pre);
+        if (p.aux) stg64(a_aux + i * s_aux, pre);
         const float4 h = unpack4_bf16(pre);
-        stg64(a_out, pack4_bf16(make_float4(gelu_tanh(h.x), gelu_tanh(h.y), gelu_tanh(h.z), gelu_tanh(h.w))));
+        stg64(ao, pack4_bf16(make_float4(gelu_tanh(h.x), gelu_tanh(h.y), gelu_tanh(h.z), gelu_tanh(h.w))));
       } else if constexpr (EPI == EPI_GATE_RESID) {
-        if (p.aux) stg64(a_aux, pack4_bf16(v));
-        const size_t b = (row0 + 4 * i) / p.rows_per_group;
-        const float4 g = ldg128_nc(gaddr(p.gate + b * p.ld_gate + col));
-        const float4 r = ldg128(a_res);  // may alias `out` (in-place residual update): plain load, read-before-write
-        stg128(a_out, make_float4(fmaf(g.x, v.x, r.x), fmaf(g.y, v.y, r.y), fmaf(g.z, v.z, r.z), fmaf(g.w, v.w, r.w)));
+        if (p.aux) stg64(a_aux + i * s_aux, pack4_bf16(v));
+        float4 g = gate4;
+        if (!gate_uniform) {
+          const size_t b = (row0 + 4 * i) / p.rows_per_group;
+          g = ldg128_nc(gaddr(p.gate + b * p.ld_gate + col));
+        }
+        const float4 r = res[i];  // may alias `out` (in-place residual update): every element is read before written
+        stg128(ao, make_float4(fmaf(g.x, v.x, r.x), fmaf(g.y, v.y, r.y), fmaf(g.z, v.z, r.z), fmaf(g.w, v.w, r.w)));
       } else if constexpr (EPI == EPI_DGELU) {
-        const float4 h = unpack4_bf16(ldg64_nc(a_aux));
-        stg64(a_out, pack4_bf16(make_float4(v.x * gelu_tanh_grad(h.x), v.y * gelu_tanh_grad(h.y),
-                                            v.z * gelu_tanh_grad(h.z), v.w * gelu_tanh_grad(h.w))));
+        const float4 h = unpack4_bf16(auxv[i]);
+        stg64(ao, pack4_bf16(make_float4(v.x * gelu_tanh_grad(h.x), v.y * gelu_tanh_grad(h.y),
+                                         v.z * gelu_tanh_grad(h.z), v.w * gelu_tanh_grad(h.w))));
       }
     }
   }

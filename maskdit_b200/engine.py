@@ -173,8 +173,11 @@ class Engine:
         return X2, saved
 
     # ------------------------------------------------------------------------------------------------------
-    def backward(self, ctx, dF16):
-        """Accumulate d(loss)/d(params) into the flat gradient buffer given dF [B*L, pd] bf16."""
+    def backward(self, ctx, dF16, on_ready=None):
+        """Accumulate d(loss)/d(params) into the flat gradient buffer given dF [B*L, pd] bf16.
+        `on_ready(lo, hi)` (optional) is called as soon as the gradient elements [lo, hi) are final, i.e. right after
+        the kernels of a block's backward have been enqueued: the training step uses it to overlap the gradient
+        all-reduce and the optimizer with the rest of the backward (what DDP buckets do in the reference)."""
         cfg, st = self.cfg, self.store
         st.ensure_grad()
         G = st.gview
@@ -197,6 +200,8 @@ class Engine:
         # ---- decoder blocks
         for spec, saved in zip(reversed(self.dec), reversed(ctx["dec"])):
             self._block_bwd(spec, saved, Gz, mod, dmod, B, L)
+            if on_ready is not None:
+                on_ready(*st.prefix_range(spec.prefix + "."))
         # ---- unmask + decoder layer
         tok_g = G("model.mask_token").view(Dd) if "model.mask_token" in st.offsets and ctx["ids_restore"] is not None \
             else None
@@ -213,6 +218,8 @@ class Engine:
         # ---- encoder blocks
         for spec, saved in zip(reversed(self.enc), reversed(ctx["enc"])):
             self._block_bwd(spec, saved, Ge, mod, dmod, B, T)
+            if on_ready is not None:
+                on_ready(*st.prefix_range(spec.prefix + "."))
         # ---- patch embedding (no input gradient needed)
         ops.patch_embed_bwd(ctx["x_in"], ctx["sigma"], cfg.sigma_data, ctx["ids_keep"], Ge.view(B, T, D),
                             G("model.x_embedder.proj.weight").view(D, -1), G("model.x_embedder.proj.bias"), p)

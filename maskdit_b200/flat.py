@@ -139,6 +139,17 @@ class FlatStore:
             self.grad = torch.zeros(self.n_train, dtype=torch.float32, device=self.device)
         return self.grad
 
+    def prefix_range(self, prefix):
+        """(lo, hi) element range of the non-adaLN trainable tensors whose key starts with `prefix` — contiguous by
+        construction (registration order), used to all-reduce / step a block's gradients as soon as they are final."""
+        items = sorted(v[:2] for k, v in self.offsets.items()
+                       if k.startswith(prefix) and "adaLN_modulation" not in k and not k.endswith("pos_embed"))
+        lo, cur = items[0][0], items[0][0]
+        for o, n in items:
+            assert o == cur, "prefix range is not contiguous"
+            cur = o + _round_up(n)
+        return lo, cur
+
     # -- bf16 shadow -------------------------------------------------------------------------------------------
     def versions(self, params: dict):
         return sum(p._version for p in params.values())

@@ -182,6 +182,7 @@ class EDMPrecond(nn.Module):
         self.model = DiT_models[model_type](input_size=img_resolution, in_channels=img_channels,
                                             num_classes=num_classes, **model_kwargs)
         self._store, self._engine, self._anchor = None, None, None
+        self._grad_ready_hook = None  # set by TrainStep: called with (lo, hi) when a gradient range is final
 
     # -- engine plumbing ---------------------------------------------------------------------------------------
     def _cfg(self):
@@ -231,7 +232,7 @@ class EDMPrecond(nn.Module):
             for k, p in params.items():
                 if p.requires_grad:
                     p.grad = st.gview(k)
-        self._engine.backward(saved, dF16)
+        self._engine.backward(saved, dF16, on_ready=self._grad_ready_hook)
 
     def __deepcopy__(self, memo):
         new = EDMPrecond(**copy.deepcopy(self._ctor))

@@ -2,11 +2,13 @@
 train_utils/helper.py:47-58 EMA).
 
 One process per GPU.  A step is:
-    zero flat grad  ->  fused EDM loss forward/backward (engine)  ->  ONE NCCL all-reduce of the flat fp32 gradient
-    buffer over NVLink (SUM; the 1/world factor is folded into the optimizer kernel)  ->  ONE fused
-    AdamW + EMA + bf16-shadow kernel over the flat buffers.
-No other collective is issued in the step; the loss is returned as a device tensor (no per-step
-`.item()` host sync as at train.py:227).
+    zero flat grad  ->  fused EDM loss forward/backward (engine)  ->  NCCL all-reduce (SUM) of the flat fp32 gradient
+    buffer over NVLink (the 1/world factor is folded into the optimizer kernel)  ->  fused AdamW + EMA + bf16-shadow
+    kernel over the flat buffers.
+With `overlap=True` (default) the flat buffer is reduced and stepped in per-block contiguous ranges on a side stream
+while the backward of the earlier blocks is still running (the role DDP's bucketed hooks play in the reference);
+with `overlap=False` it is literally one all-reduce and one optimizer launch.  No other collective is issued in the
+step; the loss is returned as a device tensor (no per-step `.item()` host sync as at train.py:227).
 """
 from __future__ import annotations
 
@@ -59,7 +61,7 @@ def lr_at(step: int, base_lr: float, global_batch: int, rampup_kimg: float):
 class TrainStep:
     def __init__(self, net: EDMPrecond, ema: EDMPrecond | None = None, lr=1e-4, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=0.0, ema_decay=0.9999, loss_fn: EDMLoss | None = None, process_group=None,
-                 lr_rampup_kimg=0.0, global_batch=None, device=None):
+                 lr_rampup_kimg=0.0, global_batch=None, device=None, overlap=True):
         self.net, self.ema = net, ema
         self.lr, self.betas, self.eps, self.wd, self.ema_decay = lr, betas, eps, weight_decay, ema_decay
         self.loss_fn = loss_fn or EDMLoss()
@@ -80,21 +82,54 @@ class TrainStep:
         for k, p in net.named_parameters():  # .grad views into the flat buffer (optimizer-compatible)
             if p.requires_grad:
                 p.grad = self.st.gview(k)
+        # Overlap: gradient ranges are reduced + stepped on a side stream as soon as a block's backward is enqueued.
+        self.overlap = overlap
+        self.side = torch.cuda.Stream(device=dev) if overlap else None
+        self._done = []          # [lo, hi) ranges already handled in the current step
+        self._lr_now = lr
+        net._grad_ready_hook = self._on_grads_ready if overlap else None
+
+    # -- one gradient range: (all-reduce) + fused AdamW/EMA/bf16-shadow, on the current stream -----------------------
+    def _reduce_and_step(self, lo, hi):
+        st, n = self.st, hi - lo
+        if n <= 0:
+            return
+        g = st.grad[lo:hi]
+        if self.world > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
+        ops.adamw_ema(st.w32[lo:hi], g, self.m[lo:hi], self.v[lo:hi],
+                      self.ema_st.w32[lo:hi] if self.ema_st is not None else None, st.w16[lo:hi], n, self._lr_now,
+                      self.step_count, self.betas[0], self.betas[1], self.eps, self.wd, self.ema_decay,
+                      1.0 / self.world)
+
+    def _on_grads_ready(self, lo, hi):
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self._reduce_and_step(lo, hi)
+        self._done.append((lo, hi))
 
     def step(self, images, labels, mask_ratio=0.5, mae_loss_coef=0.1):
         """One optimisation step on this rank's shard.  Returns the per-sample loss [B] (device tensor)."""
         st = self.st
         st.grad.zero_()
-        loss = self.loss_fn(self.net, images, labels, mask_ratio=mask_ratio, mae_loss_coef=mae_loss_coef)
-        loss.mean().backward()
-        if self.world > 1:
-            dist.all_reduce(st.grad, op=dist.ReduceOp.SUM, group=self.pg)  # the step's only collective
         self.step_count += 1
         gb = self.global_batch or images.shape[0] * self.world
-        lr = lr_at(self.step_count, self.lr, gb, self.rampup) if self.rampup > 0 else self.lr
-        ops.adamw_ema(st.w32, st.grad, self.m, self.v, self.ema_st.w32 if self.ema_st is not None else None, st.w16,
-                      st.n_train, lr, self.step_count, self.betas[0], self.betas[1], self.eps, self.wd,
-                      self.ema_decay, 1.0 / self.world)
+        self._lr_now = lr_at(self.step_count, self.lr, gb, self.rampup) if self.rampup > 0 else self.lr
+        self._done = []
+        loss = self.loss_fn(self.net, images, labels, mask_ratio=mask_ratio, mae_loss_coef=mae_loss_coef)
+        loss.mean().backward()   # engine backward; with overlap=True block ranges are already being reduced/stepped
+        main = torch.cuda.current_stream()
+        if self.overlap:
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                cur = 0
+                for lo, hi in sorted(self._done) + [(st.n_train, st.n_train)]:   # the complement of the block ranges
+                    self._reduce_and_step(cur, lo)
+                    cur = max(cur, hi)
+            main.wait_stream(self.side)
+        else:
+            self._reduce_and_step(0, st.n_train)   # one flat all-reduce + one optimizer pass
         st.mark_shadow_fresh(self.net._params())   # the kernel refreshed the bf16 shadow itself
         if self.ema_st is not None:
             self.ema_st._versions = None           # EMA weights changed behind PyTorch's back: shadow is stale

@@ -98,6 +98,13 @@ def test_flat_layout_plan():
     assert st.offsets["model.pos_embed"][0] >= st.n_train  # frozen tensors sit after the trainable region
     n_train = sum(v[1] for k, v in st.offsets.items() if not k.endswith("pos_embed"))
     assert n_train == 730_115_216  # trainable parameter count
+    # per-block gradient ranges (overlapped all-reduce/optimizer): contiguous, disjoint, inside the trainable region
+    ranges = [st.prefix_range(f"model.blocks.{i}.") for i in range(28)] + \
+             [st.prefix_range(f"model.decoder_blocks.{i}.") for i in range(8)]
+    for (a0, a1), (b0, b1) in zip(sorted(ranges), sorted(ranges)[1:]):
+        assert a0 < a1 <= b0 < b1 <= st.n_train
+    lo, hi = ranges[0]
+    assert hi - lo == 3 * 1152 * 1152 + 3456 + 1152 * 1152 + 1152 + 2 * 4608 * 1152 + 4608 + 1152
 
 
 def test_dp_helpers_and_schedule():

@@ -220,7 +220,7 @@ def bench_train(args, net, dev, world, rank, R, PK, sync_all, max_over_ranks):
     B = args.batch_per_gpu or (256 if R == 32 else 128)
     net.train()
     ema = copy.deepcopy(net).eval()
-    ts = TrainStep(net, ema, lr=1e-4, global_batch=B * world)
+    ts = TrainStep(net, ema, lr=1e-4, global_batch=B * world, overlap=os.environ.get("MDT_OVERLAP", "0") == "1")
     pool = make_batches(4, B, R, 1000, seed=rank)
     resident = [(x.to(dev), y.to(dev)) for x, y in pool]
     h2d = pool[0][0].numel() * 4 + pool[0][1].numel() * 4

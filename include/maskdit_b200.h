@@ -176,10 +176,11 @@ int mdt_heun_update(int mode, const double* x_hat, const float* denoised, double
  * Fused AdamW (weight_decay handled as adam_w_mode, train.py:141) + EMA (train_utils/helper.py:47-58) + bf16
  * weight-shadow refresh over flat buffers:  one pass instead of apex multi_tensor_adam + a 376-launch EMA loop.
  *   g is multiplied by grad_scale first (1/world_size after a SUM all-reduce).  ema / w_bf16 may be NULL.
+ *   max_blocks > 0 caps the grid (a background launch overlapped with the backward GEMMs needs only a few CTAs).
  * ------------------------------------------------------------------------------------------------------------ */
 int mdt_adamw_ema(float* w, const float* g, float* m, float* v, float* ema, void* w_bf16, long long n, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int step, float ema_decay,
-                  float grad_scale, void* stream);
+                  float grad_scale, int max_blocks, void* stream);
 
 #ifdef __cplusplus
 }

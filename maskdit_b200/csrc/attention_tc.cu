@@ -102,8 +102,12 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
   constexpr int kPBlk = (TK / 8) * 128;                       // bytes per 8-query block of P
   constexpr int kTmemCols = TK;  // O aliases S: S is dead once every row thread has written its P row to smem
   extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t sQ = smem_u32(smem), sK = sQ + kQB * DP * 2, sV = sK + TK * DP * 2, sP = sV + TK * DP * 2;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (kQB + 2 * TK) * DP * 2 + kQB * TK * 2);
+  // P may overwrite Q|K: both are dead once the S MMAs have completed (the row threads only start writing P after
+  // waiting on that commit).  For T = 128 this takes the CTA from 92 KB to 60 KB of smem -> 3 CTAs per SM.
+  constexpr bool kPAlias = kQB * TK * 2 <= (kQB + TK) * DP * 2;
+  const uint32_t sQ = smem_u32(smem), sK = sQ + kQB * DP * 2, sV = sK + TK * DP * 2;
+  const uint32_t sP = kPAlias ? sQ : sV + TK * DP * 2;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (kQB + 2 * TK) * DP * 2 + (kPAlias ? 0 : kQB * TK * 2));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -400,7 +404,8 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 template <int DP, int TK>
 static int launch_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale,
                       cudaStream_t st) {
-  const int smem = (kQB + 2 * TK) * DP * 2 + kQB * TK * 2 + 64;
+  constexpr bool kPAlias = kQB * TK * 2 <= (kQB + TK) * DP * 2;
+  const int smem = (kQB + 2 * TK) * DP * 2 + (kPAlias ? 0 : kQB * TK * 2) + 64;
   auto kern = attn_tc_fwd_kernel<DP, TK>;
   static bool set = false;
   if (!set) {

@@ -261,12 +261,13 @@ int mdt_heun_update(int mode, const double* x_hat, const float* denoised, double
 
 int mdt_adamw_ema(float* w, const float* g, float* m, float* v, float* ema, void* w_bf16, long long n, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int step, float ema_decay,
-                  float grad_scale, void* stream) {
+                  float grad_scale, int max_blocks, void* stream) {
   if (!w || !g || !m || !v || n <= 0 || step < 1 || (n & 3)) return MDT_ERR_ARG;
   const float inv_bc1 = static_cast<float>(1.0 / (1.0 - pow(static_cast<double>(beta1), step)));
   const float inv_bc2 = static_cast<float>(1.0 / (1.0 - pow(static_cast<double>(beta2), step)));
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
+  if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;
   adamw_ema_kernel<<<static_cast<int>(blocks), 256, 0, S(stream)>>>(
       w, g, m, v, ema, static_cast<__nv_bfloat16*>(w_bf16), n, lr, beta1, beta2, eps, weight_decay, inv_bc1, inv_bc2,
       ema_decay, grad_scale);

@@ -185,6 +185,6 @@ def heun_update(mode, x_hat, denoised, d_cur, x_next, x_next_f32, t_hat, t_next)
 
 
 def adamw_ema(w, g, m, v, ema, w16, n, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
-              ema_decay=0.9999, grad_scale=1.0):
+              ema_decay=0.9999, grad_scale=1.0, max_blocks=0):
     check(lib().mdt_adamw_ema(ptr(w), ptr(g), ptr(m), ptr(v), ptr(ema), ptr(w16), n, lr, beta1, beta2, eps,
-                              weight_decay, step, ema_decay, grad_scale, stream_ptr()), "mdt_adamw_ema")
+                              weight_decay, step, ema_decay, grad_scale, max_blocks, stream_ptr()), "mdt_adamw_ema")

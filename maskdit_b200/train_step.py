@@ -5,9 +5,10 @@ One process per GPU.  A step is:
     zero flat grad  ->  fused EDM loss forward/backward (engine)  ->  NCCL all-reduce (SUM) of the flat fp32 gradient
     buffer over NVLink (the 1/world factor is folded into the optimizer kernel)  ->  fused AdamW + EMA + bf16-shadow
     kernel over the flat buffers.
-With `overlap=True` (default) the flat buffer is reduced and stepped in per-block contiguous ranges on a side stream
+With `overlap=True` the flat buffer is reduced and stepped in per-block contiguous ranges on a side stream
 while the backward of the earlier blocks is still running (the role DDP's bucketed hooks play in the reference);
-with `overlap=False` it is literally one all-reduce and one optimizer launch.  No other collective is issued in the
+with `overlap=False` (default: measured equal or faster up to 2 GPUs, see profiles/README.md) it is literally one
+all-reduce and one optimizer launch.  No other collective is issued in the
 step; the loss is returned as a device tensor (no per-step `.item()` host sync as at train.py:227).
 """
 from __future__ import annotations
@@ -61,7 +62,7 @@ def lr_at(step: int, base_lr: float, global_batch: int, rampup_kimg: float):
 class TrainStep:
     def __init__(self, net: EDMPrecond, ema: EDMPrecond | None = None, lr=1e-4, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=0.0, ema_decay=0.9999, loss_fn: EDMLoss | None = None, process_group=None,
-                 lr_rampup_kimg=0.0, global_batch=None, device=None, overlap=True):
+                 lr_rampup_kimg=0.0, global_batch=None, device=None, overlap=False):
         self.net, self.ema = net, ema
         self.lr, self.betas, self.eps, self.wd, self.ema_decay = lr, betas, eps, weight_decay, ema_decay
         self.loss_fn = loss_fn or EDMLoss()
@@ -84,13 +85,14 @@ class TrainStep:
                 p.grad = self.st.gview(k)
         # Overlap: gradient ranges are reduced + stepped on a side stream as soon as a block's backward is enqueued.
         self.overlap = overlap
+        self.bg_blocks = 24
         self.side = torch.cuda.Stream(device=dev) if overlap else None
         self._done = []          # [lo, hi) ranges already handled in the current step
         self._lr_now = lr
         net._grad_ready_hook = self._on_grads_ready if overlap else None
 
     # -- one gradient range: (all-reduce) + fused AdamW/EMA/bf16-shadow, on the current stream -----------------------
-    def _reduce_and_step(self, lo, hi):
+    def _reduce_and_step(self, lo, hi, max_blocks=0):
         st, n = self.st, hi - lo
         if n <= 0:
             return
@@ -100,13 +102,15 @@ class TrainStep:
         ops.adamw_ema(st.w32[lo:hi], g, self.m[lo:hi], self.v[lo:hi],
                       self.ema_st.w32[lo:hi] if self.ema_st is not None else None, st.w16[lo:hi], n, self._lr_now,
                       self.step_count, self.betas[0], self.betas[1], self.eps, self.wd, self.ema_decay,
-                      1.0 / self.world)
+                      1.0 / self.world, max_blocks)
 
     def _on_grads_ready(self, lo, hi):
         main = torch.cuda.current_stream()
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
-            self._reduce_and_step(lo, hi)
+            # background launch: a block's optimizer pass needs <2 % of the HBM bandwidth to finish before the backward
+            # does, so it is capped to a few CTAs and leaves the SMs to the tensor-core GEMMs
+            self._reduce_and_step(lo, hi, max_blocks=self.bg_blocks)
         self._done.append((lo, hi))
 
     def step(self, images, labels, mask_ratio=0.5, mae_loss_coef=0.1):

@@ -45,7 +45,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
 
     def run(job):
         src, obj = job
-        cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
+        cmd = [NVCC, *FLAGS, *os.environ.get("MDT_NVCC_EXTRA", "").split(), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")

@@ -38,6 +38,37 @@ MDT_DEVINL void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+MDT_DEVINL void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+// N consecutive fp32 columns (N % 8 == 0, N <= 96) of this thread's TMEM lane -> registers, ONE wait at the end
+template <int N>
+MDT_DEVINL void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
+  int c = 0;
+#pragma unroll
+  for (; c + 32 <= N; c += 32) tmem_ld_32x32b_x32(taddr + c, r + c);
+  if (N - c >= 16) {
+    tmem_ld_32x32b_x16(taddr + c, r + c);
+    c += 16;
+  }
+  if (N - c >= 8) tmem_ld_32x32b_x8(taddr + c, r + c);
+  tcgen05_wait_ld();
+}
+// store N fp32 values as bf16 to a global row, 16 bytes at a time, columns >= dh dropped
+template <int N>
+MDT_DEVINL void store_row_bf16(__nv_bfloat16* grow, int col0, const uint32_t* r, int dh, float mul) {
+#pragma unroll
+  for (int g = 0; g < N / 8; ++g)
+    if (col0 + 8 * g < dh)
+      *reinterpret_cast<uint4*>(grow + col0 + 8 * g) = make_uint4(
+          pack_bf16(__uint_as_float(r[8 * g + 0]) * mul, __uint_as_float(r[8 * g + 1]) * mul),
+          pack_bf16(__uint_as_float(r[8 * g + 2]) * mul, __uint_as_float(r[8 * g + 3]) * mul),
+          pack_bf16(__uint_as_float(r[8 * g + 4]) * mul, __uint_as_float(r[8 * g + 5]) * mul),
+          pack_bf16(__uint_as_float(r[8 * g + 6]) * mul, __uint_as_float(r[8 * g + 7]) * mul));
+}
 MDT_DEVINL void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -66,7 +97,7 @@ struct TokTile {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = lane & 7, cl = lane >> 3;
     const int items = (rows >> 3) * CG4;
-    for (int it = warp; it < items; it += kQB / 32) {
+    for (int it = warp; it < items; it += blockDim.x >> 5) {
       const int rb = it / CG4, cg = it - rb * CG4;
       const int c8 = cg * 4 + cl, row = rb * 8 + r;
       if (c8 < CH) {
@@ -186,22 +217,10 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
   const float inv_l = 1.f / l;
   const int q = q0 + tid;
   __nv_bfloat16* orow = out + (static_cast<long long>(b) * T + q) * (H * dh) + h * dh;
-#pragma unroll
-  for (int c = 0; c < DP; c += 16) {
-    uint32_t r[16];
-    tmem_ld_32x32b_x16(tO + lane_addr + c, r);
-    tcgen05_wait_ld();
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      if (c + 8 * g < dh) {
-        const uint4 v = make_uint4(
-            pack_bf16(__uint_as_float(r[8 * g + 0]) * inv_l, __uint_as_float(r[8 * g + 1]) * inv_l),
-            pack_bf16(__uint_as_float(r[8 * g + 2]) * inv_l, __uint_as_float(r[8 * g + 3]) * inv_l),
-            pack_bf16(__uint_as_float(r[8 * g + 4]) * inv_l, __uint_as_float(r[8 * g + 5]) * inv_l),
-            pack_bf16(__uint_as_float(r[8 * g + 6]) * inv_l, __uint_as_float(r[8 * g + 7]) * inv_l));
-        *reinterpret_cast<uint4*>(orow + c + 8 * g) = v;
-      }
-    }
+  {
+    uint32_t r[DP];
+    tmem_ld_cols<DP>(tO + lane_addr, r);
+    store_row_bf16<DP>(orow, 0, r, dh, inv_l);
   }
   if (lse) lse[(static_cast<long long>(b) * H + h) * T + q] = m * scale + logf(l);
   tcgen05_fence_before();
@@ -215,187 +234,226 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
 // ------------------------------------------------------------------------------------------------------------
 // backward (one CTA per (b,h); NB = T / 128 query blocks == key blocks)
 // ------------------------------------------------------------------------------------------------------------
+constexpr int kBwdThreads = 256;  // two threads per query / key row: each owns half of the columns of every phase
+
+// Persistent: one CTA per SM walks the (b,h) items; the Q/K/V/dO tiles of item i+1 are fetched with cp.async into the
+// second tile set while item i is being computed (a per-item CTA spent 8k of its 18k cycles waiting for its tiles).
+// delta = rowsum(dO * O):  NB == 1 uses the identity  sum_d dO*O = sum_k P*dP  on the S / dP accumulators already in
+// TMEM (no O tile at all); NB == 2 stages O as a fifth tile of the set.
 template <int DP, int NB>
-__global__ void __launch_bounds__(kQB)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                    const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
-                   __nv_bfloat16* __restrict__ dqkv, int H, int dh, float scale) {
+                   __nv_bfloat16* __restrict__ dqkv, int H, int dh, float scale, int nitems) {
   using TT = TokTile<DP>;
   constexpr int T = NB * kQB;
+  constexpr bool kDeltaFromP = NB == 1;
   constexpr int kPBlk = (kQB / 8) * 128;  // P / dS tiles are [128 queries x 128 keys]
   constexpr int kTileBytes = T * DP * 2;
+  constexpr int kSetTiles = kDeltaFromP ? 4 : 5;
+  constexpr int kSetBytes = kSetTiles * kTileBytes;
   static_assert(256 + DP + 2 * NB * DP <= 512, "TMEM budget");
+  static_assert(NB <= 2, "delta/lse selection below assumes at most two query blocks");
   extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t sQ = smem_u32(smem), sK = sQ + kTileBytes, sV = sK + kTileBytes, sdO = sV + kTileBytes;
-  const uint32_t sP = sdO + kTileBytes, sdS = sP + kQB * kQB * 2;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 4 * kTileBytes + 2 * kQB * kQB * 2);
+  const uint32_t s0 = smem_u32(smem);
+  const uint32_t sP = s0 + 2 * kSetBytes, sdS = sP + kQB * kQB * 2;
+  float* s_part = reinterpret_cast<float*>(smem + 2 * kSetBytes + 2 * kQB * kQB * 2);  // [2][128] partial deltas
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_part + 2 * kQB);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int row = tid & (kQB - 1), half = tid >> 7;  // TMEM lane (= row) is fixed by warp % 4, `half` picks the columns
   const long long rs = 3LL * H * dh;
   const int HD = H * dh;
-  const __nv_bfloat16* base = qkv + static_cast<long long>(b) * T * rs;
   if (warp == 0) tmem_alloc<512>(tmem_slot);
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
   }
-  TT::load(sQ, base + h * dh, rs, T, dh);
-  TT::load(sK, base + (H + h) * dh, rs, T, dh);
-  TT::load(sV, base + (2 * H + h) * dh, rs, T, dh);
-  TT::load(sdO, dout + static_cast<long long>(b) * T * HD + h * dh, HD, T, dh);
-  cp_async_wait_all();
-  fence_proxy_async_smem();
+  auto issue_loads = [&](int item, uint32_t set) {
+    const int b = item / H, h = item % H;
+    const __nv_bfloat16* base = qkv + static_cast<long long>(b) * T * rs;
+    TT::load(set, base + h * dh, rs, T, dh);
+    TT::load(set + kTileBytes, base + (H + h) * dh, rs, T, dh);
+    TT::load(set + 2 * kTileBytes, base + (2 * H + h) * dh, rs, T, dh);
+    TT::load(set + 3 * kTileBytes, dout + static_cast<long long>(b) * T * HD + h * dh, HD, T, dh);
+    if constexpr (!kDeltaFromP) TT::load(set + 4 * kTileBytes, out + static_cast<long long>(b) * T * HD + h * dh, HD, T, dh);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int item = blockIdx.x;
+  if (item < nitems) issue_loads(item, s0);
+  float lse_next[NB];
+#pragma unroll
+  for (int qb = 0; qb < NB; ++qb)
+    lse_next[qb] = item < nitems ? lse[static_cast<long long>(item) * T + qb * kQB + row] : 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256, tKV = tmem + 256 + DP;  // dK[j] | dV[j] at tKV + j*2DP
-  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const float sl = scale * 1.4426950408889634f;
   constexpr uint32_t RB = TT::ROWBLK;
   constexpr uint32_t kBlkBytes = 16 * RB;  // 128 token rows
   uint32_t phase = 0;
 
-  if (tid == 0) {  // first S / dP
-    mma_kk<DP>(tS, sQ, sK, kQB, false);
-    mma_kk<DP>(tdP, sdO, sV, kQB, false);
-    umma_commit(bar);
-  }
-  for (int qb = 0; qb < NB; ++qb) {
-    const int q = qb * kQB + tid;
-    // delta = rowsum(dO * O), lse of this query row
-    float delta = 0.f;
-    {
-      const __nv_bfloat16* orow = out + (static_cast<long long>(b) * T + q) * HD + h * dh;
-      const __nv_bfloat16* drow = dout + (static_cast<long long>(b) * T + q) * HD + h * dh;
-      uint4 a[DP / 8], d[DP / 8];
+  for (int it = 0; item < nitems; ++it, item += gridDim.x) {
+    const uint32_t set = s0 + (it & 1) * kSetBytes;
+    const uint32_t sQ = set, sK = set + kTileBytes, sV = set + 2 * kTileBytes, sdO = set + 3 * kTileBytes;
+    const int b = item / H, h = item % H;
+    const int nxt = item + gridDim.x;
+    float lse_all[NB];
 #pragma unroll
-      for (int c = 0; c < DP / 8; ++c) {
-        a[c] = d[c] = make_uint4(0, 0, 0, 0);
-        if (c * 8 < dh) a[c] = ldg128u_nc(orow + c * 8), d[c] = ldg128u_nc(drow + c * 8);
-      }
+    for (int qb = 0; qb < NB; ++qb) lse_all[qb] = lse_next[qb];
+    // prefetch the next item into the other set (its last readers, the MMAs of item it-1, completed before that item's
+    // read-out) and this row's next lse values
+    if (nxt < nitems) {
+      issue_loads(nxt, s0 + ((it + 1) & 1) * kSetBytes);
 #pragma unroll
-      for (int c = 0; c < DP / 8; ++c)
-        delta += bf16_lo(a[c].x) * bf16_lo(d[c].x) + bf16_hi(a[c].x) * bf16_hi(d[c].x) +
-                 bf16_lo(a[c].y) * bf16_lo(d[c].y) + bf16_hi(a[c].y) * bf16_hi(d[c].y) +
-                 bf16_lo(a[c].z) * bf16_lo(d[c].z) + bf16_hi(a[c].z) * bf16_hi(d[c].z) +
-                 bf16_lo(a[c].w) * bf16_lo(d[c].w) + bf16_hi(a[c].w) * bf16_hi(d[c].w);
+      for (int qb = 0; qb < NB; ++qb) lse_next[qb] = lse[static_cast<long long>(nxt) * T + qb * kQB + row];
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    const float lsl = lse[(static_cast<long long>(b) * H + h) * T + q] * 1.4426950408889634f;
-    for (int kb = 0; kb < NB; ++kb) {
-      mbar_wait(bar, phase);
-      phase ^= 1;
-      tcgen05_fence_after();
-      const uint32_t prow = (tid >> 3) * kPBlk + (tid & 7) * 16;
-#pragma unroll 1
-      for (int c = 0; c < kQB; c += 32) {
-        uint32_t rs_[32], rp[32];
-        tmem_ld_32x32b_x32(tS + lane_addr + c, rs_);
-        tmem_ld_32x32b_x32(tdP + lane_addr + c, rp);
-        tcgen05_wait_ld();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float p[8], ds[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            p[j] = exp2f(__uint_as_float(rs_[8 * g + j]) * sl - lsl);
-            ds[j] = p[j] * (__uint_as_float(rp[8 * g + j]) - delta) * scale;
-          }
-          const uint32_t o = prow + (c / 8 + g) * 128;
-          sts128u(sP + o, make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]),
-                                     pack_bf16(p[6], p[7])));
-          sts128u(sdS + o, make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]),
-                                      pack_bf16(ds[6], ds[7])));
-        }
-      }
-      fence_proxy_async_smem();
-      tcgen05_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tcgen05_fence_after();
-        const uint32_t tdK = tKV + kb * 2 * DP, tdV = tdK + DP;
-        const uint32_t i_tt = make_idesc_bf16(kQB, DP, 1, 1);  // A, B both token-contracted (MN-major)
-        const uint32_t i_kt = make_idesc_bf16(kQB, DP, 0, 1);  // A K-major (keys contiguous), B token-contracted
-#pragma unroll
-        for (int k = 0; k < kQB / 16; ++k) {
-          // dV[kb] += P^T dO[qb] ; dK[kb] += dS^T Q[qb]   (contraction over the 128 queries)
-          const uint64_t aP = make_smem_desc_nosw(sP + k * 2 * kPBlk, kPBlk, 128);
-          const uint64_t aS = make_smem_desc_nosw(sdS + k * 2 * kPBlk, kPBlk, 128);
-          const uint64_t bO = make_smem_desc_nosw(sdO + qb * kBlkBytes + k * 2 * RB, RB, 128);
-          const uint64_t bQ = make_smem_desc_nosw(sQ + qb * kBlkBytes + k * 2 * RB, RB, 128);
-          umma_bf16(tdV, aP, bO, i_tt, (qb > 0 || k > 0) ? 1u : 0u);
-          umma_bf16(tdK, aS, bQ, i_tt, (qb > 0 || k > 0) ? 1u : 0u);
-          // dQ[qb] += dS K[kb]   (contraction over the 128 keys)
-          const uint64_t aS2 = make_smem_desc_nosw(sdS + k * 256, 128, kPBlk);
-          const uint64_t bK = make_smem_desc_nosw(sK + kb * kBlkBytes + k * 2 * RB, RB, 128);
-          umma_bf16(tdQ, aS2, bK, i_kt, (kb > 0 || k > 0) ? 1u : 0u);
-        }
-        // next (qb, kb): S and dP can be issued right away, one commit covers everything issued so far
-        int nq = qb, nk = kb + 1;
-        if (nk == NB) nk = 0, ++nq;
-        if (nq < NB) {
-          mma_kk<DP>(tS, sQ + nq * kBlkBytes, sK + nk * kBlkBytes, kQB, false);
-          mma_kk<DP>(tdP, sdO + nq * kBlkBytes, sV + nk * kBlkBytes, kQB, false);
-        }
-        umma_commit(bar);
-      }
-    }
-    // dQ of this query block is complete once the last commit lands; the same commit also covers the next S/dP
-    mbar_wait(bar, phase);
-    tcgen05_fence_after();
-    __nv_bfloat16* grow = dqkv + (static_cast<long long>(b) * T + q) * rs + h * dh;
-#pragma unroll
-    for (int c = 0; c < DP; c += 16) {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(tdQ + lane_addr + c, r);
-      tcgen05_wait_ld();
-#pragma unroll
-      for (int g = 0; g < 2; ++g)
-        if (c + 8 * g < dh)
-          *reinterpret_cast<uint4*>(grow + c + 8 * g) = make_uint4(
-              pack_bf16(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1])),
-              pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3])),
-              pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5])),
-              pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7])));
-    }
-    // the next iteration's first wait uses the same (already completed) phase: do not flip here
+    fence_proxy_async_smem();
     tcgen05_fence_before();
-    __syncthreads();  // all rows read dQ before the next query block's MMAs (already queued behind this commit) reuse it
-  }
-  // dK / dV: rows = keys
-#pragma unroll 1
-  for (int kb = 0; kb < NB; ++kb) {
-    const int key = kb * kQB + tid;
-    __nv_bfloat16* krow = dqkv + (static_cast<long long>(b) * T + key) * rs + (H + h) * dh;
-    __nv_bfloat16* vrow = dqkv + (static_cast<long long>(b) * T + key) * rs + (2 * H + h) * dh;
+    __syncthreads();
+    tcgen05_fence_after();
+
+    float delta_all[NB];
+    if constexpr (!kDeltaFromP) {
+      const uint32_t sO = set + 4 * kTileBytes;
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      __nv_bfloat16* grow = which ? vrow : krow;
-      const uint32_t tacc = tKV + kb * 2 * DP + which * DP;
+      for (int qb = 0; qb < NB; ++qb) {
+        const int q = qb * kQB + row;
+        float acc = 0.f;
 #pragma unroll
-      for (int c = 0; c < DP; c += 16) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(tacc + lane_addr + c, r);
-        tcgen05_wait_ld();
-#pragma unroll
-        for (int g = 0; g < 2; ++g)
-          if (c + 8 * g < dh)
-            *reinterpret_cast<uint4*>(grow + c + 8 * g) = make_uint4(
-                pack_bf16(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1])),
-                pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3])),
-                pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5])),
-                pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7])));
+        for (int c = 0; c < DP / 8; ++c) {
+          uint4 a, d;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(sO + TT::off(q, c)));
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "r"(sdO + TT::off(q, c)));
+          acc += bf16_lo(a.x) * bf16_lo(d.x) + bf16_hi(a.x) * bf16_hi(d.x) + bf16_lo(a.y) * bf16_lo(d.y) +
+                 bf16_hi(a.y) * bf16_hi(d.y) + bf16_lo(a.z) * bf16_lo(d.z) + bf16_hi(a.z) * bf16_hi(d.z) +
+                 bf16_lo(a.w) * bf16_lo(d.w) + bf16_hi(a.w) * bf16_hi(d.w);
+        }
+        delta_all[qb] = acc;
       }
     }
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 0) {
+    if (tid == 0) {  // first S / dP of this item
+      mma_kk<DP>(tS, sQ, sK, kQB, false);
+      mma_kk<DP>(tdP, sdO, sV, kQB, false);
+      umma_commit(bar);
+    }
+    for (int qb = 0; qb < NB; ++qb) {
+      const int q = qb * kQB + row;
+      float delta = kDeltaFromP ? 0.f : (qb == 0 ? delta_all[0] : delta_all[NB - 1]);
+      const float lsl = (qb == 0 ? lse_all[0] : lse_all[NB - 1]) * 1.4426950408889634f;
+      for (int kb = 0; kb < NB; ++kb) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tcgen05_fence_after();
+        if constexpr (kDeltaFromP) {
+          // delta_q = sum_k P[q,k] dP[q,k]; the two threads of a row each sum their 64 keys and meet through smem
+          float part = 0.f;
+#pragma unroll 1
+          for (int c = half * (kQB / 2); c < (half + 1) * (kQB / 2); c += 32) {
+            uint32_t rs_[32], rp[32];
+            tmem_ld_32x32b_x32(tS + lane_addr + c, rs_);
+            tmem_ld_32x32b_x32(tdP + lane_addr + c, rp);
+            tcgen05_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              part = fmaf(exp2f(__uint_as_float(rs_[j]) * sl - lsl), __uint_as_float(rp[j]), part);
+          }
+          s_part[half * kQB + row] = part;
+          __syncthreads();
+          delta = s_part[row] + s_part[kQB + row];
+        }
+        const uint32_t prow = (row >> 3) * kPBlk + (row & 7) * 16;
+#pragma unroll 1
+        for (int c = half * (kQB / 2); c < (half + 1) * (kQB / 2); c += 32) {
+          uint32_t rs_[32], rp[32];
+          tmem_ld_32x32b_x32(tS + lane_addr + c, rs_);
+          tmem_ld_32x32b_x32(tdP + lane_addr + c, rp);
+          tcgen05_wait_ld();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float p[8], ds[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              p[j] = exp2f(__uint_as_float(rs_[8 * g + j]) * sl - lsl);
+              ds[j] = p[j] * (__uint_as_float(rp[8 * g + j]) - delta) * scale;
+            }
+            const uint32_t o = prow + (c / 8 + g) * 128;
+            sts128u(sP + o, make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]),
+                                       pack_bf16(p[6], p[7])));
+            sts128u(sdS + o, make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]),
+                                        pack_bf16(ds[6], ds[7])));
+          }
+        }
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+          tcgen05_fence_after();
+          const uint32_t tdK = tKV + kb * 2 * DP, tdV = tdK + DP;
+          const uint32_t i_tt = make_idesc_bf16(kQB, DP, 1, 1);  // A, B both token-contracted (MN-major)
+          const uint32_t i_kt = make_idesc_bf16(kQB, DP, 0, 1);  // A K-major (keys contiguous), B token-contracted
+#pragma unroll
+          for (int k = 0; k < kQB / 16; ++k) {
+            // dV[kb] += P^T dO[qb] ; dK[kb] += dS^T Q[qb]   (contraction over the 128 queries)
+            const uint64_t aP = make_smem_desc_nosw(sP + k * 2 * kPBlk, kPBlk, 128);
+            const uint64_t aS = make_smem_desc_nosw(sdS + k * 2 * kPBlk, kPBlk, 128);
+            const uint64_t bO = make_smem_desc_nosw(sdO + qb * kBlkBytes + k * 2 * RB, RB, 128);
+            const uint64_t bQ = make_smem_desc_nosw(sQ + qb * kBlkBytes + k * 2 * RB, RB, 128);
+            umma_bf16(tdV, aP, bO, i_tt, (qb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tdK, aS, bQ, i_tt, (qb > 0 || k > 0) ? 1u : 0u);
+            // dQ[qb] += dS K[kb]   (contraction over the 128 keys)
+            const uint64_t aS2 = make_smem_desc_nosw(sdS + k * 256, 128, kPBlk);
+            const uint64_t bK = make_smem_desc_nosw(sK + kb * kBlkBytes + k * 2 * RB, RB, 128);
+            umma_bf16(tdQ, aS2, bK, i_kt, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          // next (qb, kb) of this item: S and dP can be issued right away, one commit covers everything issued so far
+          int nq = qb, nk = kb + 1;
+          if (nk == NB) nk = 0, ++nq;
+          if (nq < NB) {
+            mma_kk<DP>(tS, sQ + nq * kBlkBytes, sK + nk * kBlkBytes, kQB, false);
+            mma_kk<DP>(tdP, sdO + nq * kBlkBytes, sV + nk * kBlkBytes, kQB, false);
+          }
+          umma_commit(bar);
+        }
+      }
+      // dQ of this query block is complete once the last commit lands; the same commit also covers the next S/dP
+      mbar_wait(bar, phase);
+      tcgen05_fence_after();
+      __nv_bfloat16* grow = dqkv + (static_cast<long long>(b) * T + q) * rs + h * dh;
+      {
+        // the two threads of a row take the two column halves (DP/2 is a multiple of 8 for DP = 32, 64, 80)
+        constexpr int HC = DP / 2;
+        uint32_t r[HC];
+        tmem_ld_cols<HC>(tdQ + lane_addr + half * HC, r);
+        store_row_bf16<HC>(grow, half * HC, r, dh, 1.f);
+      }
+      // the next iteration's first wait uses the same (already completed) phase: do not flip here
+      tcgen05_fence_before();
+      __syncthreads();  // all rows read dQ before the next query block's MMAs (queued behind this commit) reuse it
+    }
+    phase ^= 1;  // the last commit of the item has been consumed by the wait above
+    // dK / dV: rows = keys; threads 0-127 write dK, threads 128-255 write dV
+#pragma unroll 1
+    for (int kb = 0; kb < NB; ++kb) {
+      const int key = kb * kQB + row;
+      __nv_bfloat16* grow = dqkv + (static_cast<long long>(b) * T + key) * rs + ((1 + half) * H + h) * dh;
+      const uint32_t tacc = tKV + kb * 2 * DP + half * DP;
+      uint32_t r[DP];
+      tmem_ld_cols<DP>(tacc + lane_addr, r);
+      store_row_bf16<DP>(grow, 0, r, dh, 1.f);
+    }
+    tcgen05_fence_before();
+    __syncthreads();  // accumulators and tiles of this item are dead; the next item may overwrite them
     tcgen05_fence_after();
-    tmem_dealloc<512>(tmem);
   }
+  if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -419,16 +477,23 @@ static int launch_fwd(const void* qkv, void* out, float* lse, int B, int T, int 
 template <int DP, int NB>
 static int launch_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int H,
                       int dh, float scale, cudaStream_t st) {
-  const int smem = 4 * NB * kQB * DP * 2 + 2 * kQB * kQB * 2 + 64;
+  constexpr int kSetTiles = (NB == 1) ? 4 : 5;
+  const int smem = 2 * kSetTiles * NB * kQB * DP * 2 + 2 * kQB * kQB * 2 + 2 * kQB * 4 + 64;
   auto kern = attn_tc_bwd_kernel<DP, NB>;
   static bool set = false;
+  static int sms = 0;
   if (!set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return MDT_ERR_CUDA;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = kNumSMsDefault;
     set = true;
   }
-  kern<<<B * H, kQB, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
-                                 static_cast<const __nv_bfloat16*>(dout), lse, static_cast<__nv_bfloat16*>(dqkv), H, dh,
-                                 scale);
+  const int nitems = B * H;
+  kern<<<nitems < sms ? nitems : sms, kBwdThreads, smem, st>>>(
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
+      static_cast<const __nv_bfloat16*>(dout), lse, static_cast<__nv_bfloat16*>(dqkv), H, dh, scale, nitems);
   return cudaGetLastError() == cudaSuccess ? MDT_OK : MDT_ERR_CUDA;
 }
 

@@ -296,7 +296,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t phase = 0;
     while (sched.next()) {
       const int m0 = sched.m_tile() * TILE_M + cta_rank * BLOCK_M;
-      const int n0 = sched.n_tile() * BLOCK_N + cta_rank * Cfg::kBRows;
+      // ragged last column tile: when <= BLOCK_N/2 columns remain the MMA runs at half width (see the issuer), and the
+      // CTAs of a pair split THAT width (rows beyond N are zero-filled by TMA and never touch DRAM)
+      const int nt0 = sched.n_tile() * BLOCK_N;
+      const bool narrow = BLOCK_N == 256 && (p.N - nt0) <= BLOCK_N / 2;
+      const int n0 = nt0 + cta_rank * (narrow ? Cfg::kBRows / 2 : Cfg::kBRows);
       for (int kb = sched.kb0; kb < sched.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem_tiles + stage * Cfg::kStageBytes;
@@ -329,7 +333,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == 1 && lane == 0 && leader) {
     // ===================== MMA issuer (leader CTA only) =====================
-    constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint32_t idesc_full = make_idesc_bf16(TILE_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint32_t idesc_half = make_idesc_bf16(TILE_M, BLOCK_N / 2, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -338,6 +343,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+      const bool narrow = BLOCK_N == 256 && (p.N - sched.n_tile() * BLOCK_N) <= BLOCK_N / 2;
+      const uint32_t idesc = narrow ? idesc_half : idesc_full;  // half-width MMAs on a ragged last column tile
       for (int kb = sched.kb0; kb < sched.kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();

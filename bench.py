@@ -288,7 +288,11 @@ def bench_train(args, net, dev, world, rank, R, PK, sync_all, max_over_ranks):
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all GEMM launches of one step)",
                      "achieved": achieved, "peak": PK["sustained"], "unit": "TFLOP/s",
                      "frac": achieved / PK["sustained"], "peak_source": f"{PK['src']} sustained bf16",
-                     "traffic": None, "launches_per_step": len(prof), "share_of_step": gemm_ms / ms_step,
+                     # DRAM read+write bytes per launch from the committed `ncu --set full` capture of four consecutive
+                     # launches of this kernel inside a step (profiles/r01_gemm_ncu_full_v2.json: 646, 741, 268,
+                     # 421 MB against 690, 690, 310, 456 MB algorithmic) - average, bytes
+                     "traffic": 519e6 if R == 32 and B == 256 else None,
+                     "launches_per_step": len(prof), "share_of_step": gemm_ms / ms_step,
                      "step_achieved": sps / world * flop / 1e12, "step_frac": sps / world * flop / 1e12 / PK["sustained"]},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -168,8 +168,10 @@ def test_xl2_config1_forward_vs_reference_golden():
     assert torch.allclose(loss.cpu(), g["loss"], rtol=1e-2)
 
 
-def test_train_step_matches_oracle_adamw_and_ema():
-    """Full step (loss fwd/bwd + AdamW + EMA) for 2 steps vs the CPU oracle; also deepcopy/state_dict round trip."""
+@pytest.mark.parametrize("overlap", [False, True])
+def test_train_step_matches_oracle_adamw_and_ema(overlap):
+    """Full step (loss fwd/bwd + AdamW + EMA) for 2 steps vs the CPU oracle; also deepcopy/state_dict round trip.
+    overlap=True exercises the per-block side-stream reduce+step path."""
     from maskdit_b200.train_step import TrainStep
     from oracle import maskdit_oracle as O
     g = load("s2_train_mask")
@@ -177,7 +179,7 @@ def test_train_step_matches_oracle_adamw_and_ema():
     net.train()
     ema = copy.deepcopy(net).eval()
     assert set(ema.state_dict().keys()) == set(sd.keys())
-    ts = TrainStep(net, ema, lr=1e-3, loss_fn=None)
+    ts = TrainStep(net, ema, lr=1e-3, loss_fn=None, overlap=overlap)
     sdr = {k: v.clone().requires_grad_(not k.endswith("pos_embed")) for k, v in sd.items()}
     er = {k: v.clone() for k, v in sd.items()}
     mo = {k: torch.zeros_like(v) for k, v in sd.items()}

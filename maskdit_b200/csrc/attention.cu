@@ -361,6 +361,11 @@ namespace mdt {
 int attention_tc_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale, cudaStream_t st);
 int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int T,
                      int H, int dh, float scale, cudaStream_t st);
+// attention_tc_long.cu: T = 512 / 1024 (and the T = 256 backward the persistent kernel does not cover)
+int attention_tc_long_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale,
+                          cudaStream_t st);
+int attention_tc_long_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
+                          void* dqkv, int B, int T, int H, int dh, float scale, cudaStream_t st);
 }  // namespace mdt
 
 using namespace mdt;
@@ -369,6 +374,15 @@ static bool use_tc() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MDT_ATTN_TC");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static bool use_tc_long() {  // MDT_ATTN_LONG=0: T >= 512 stays on the mma.sync kernels (A/B switch)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MDT_ATTN_LONG");
     v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
@@ -400,8 +414,12 @@ int mdt_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int 
   dim3 grid((T + kTile - 1) / kTile, B * H);
   const float scale = 1.f / sqrtf(static_cast<float>(dh));
   if (use_tc()) {
-    const int rc = attention_tc_fwd(qkv, out, lse, B, T, H, dh, scale, static_cast<cudaStream_t>(stream));
+    int rc = attention_tc_fwd(qkv, out, lse, B, T, H, dh, scale, static_cast<cudaStream_t>(stream));
     if (rc != MDT_ERR_UNSUPPORTED) return rc;
+    if (use_tc_long()) {
+      rc = attention_tc_long_fwd(qkv, out, lse, B, T, H, dh, scale, static_cast<cudaStream_t>(stream));
+      if (rc != MDT_ERR_UNSUPPORTED) return rc;
+    }
   }
   MDT_DP_DISPATCH(dp, attn_fwd_kernel<kDP><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
                           static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, T, H, dh,
@@ -420,8 +438,12 @@ int mdt_attention_bwd(const void* qkv, const void* out, const void* dout, const 
   float* delta = const_cast<float*>(lse) + static_cast<size_t>(B) * H * T;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_tc()) {
-    const int rc = attention_tc_bwd(qkv, out, dout, lse, dqkv, B, T, H, dh, scale, st);
+    int rc = attention_tc_bwd(qkv, out, dout, lse, dqkv, B, T, H, dh, scale, st);
     if (rc != MDT_ERR_UNSUPPORTED) return rc;
+    if (use_tc_long()) {
+      rc = attention_tc_long_bwd(qkv, out, dout, lse, delta, dqkv, B, T, H, dh, scale, st);
+      if (rc != MDT_ERR_UNSUPPORTED) return rc;
+    }
   }
   MDT_DP_DISPATCH(dp, {
     attn_bwd_dq_kernel<kDP><<<grid, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv),

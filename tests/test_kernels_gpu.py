@@ -234,7 +234,8 @@ def attn_ref(qkv, B, T, H, dh):
 
 @pytest.mark.parametrize("B,T,H,dh", [(2, 128, 16, 72), (2, 256, 16, 32), (3, 8, 6, 64), (1, 200, 4, 72),
                                       (1, 512, 16, 72), (1, 1024, 2, 32), (2, 256, 16, 72), (3, 128, 6, 64),
-                                      (5, 128, 16, 32)])
+                                      (5, 128, 16, 32), (2, 512, 4, 32), (1, 512, 6, 64), (1, 1024, 3, 64),
+                                      (1, 1024, 2, 72), (3, 256, 5, 64)])
 def test_attention_fwd_bwd(ops, B, T, H, dh):
     torch.manual_seed(8)
     qkv = rb(B * T, 3 * H * dh)

@@ -265,8 +265,8 @@ def bench_train(args, net, dev, world, rank, R, PK, sync_all, max_over_ranks):
     step_resident(0)
     torch.cuda.synchronize()
     prof, _lib.GEMM_PROFILE = _lib.GEMM_PROFILE, None
-    gemm_ms = sum(a.elapsed_time(b) for _, a, b in prof)
-    gemm_flops = sum(f for f, _, _ in prof)
+    gemm_ms = sum(a.elapsed_time(b) for _, a, b, _k in prof)
+    gemm_flops = sum(f for f, _, _, _k in prof)
     ms_step = ms / args.steps
     sps = B * world * args.steps / (ms / 1e3)
     sps_e2e = B * world * args.steps / (ms_e2e / 1e3)

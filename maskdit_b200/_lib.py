@@ -11,7 +11,8 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmaskdit_b200.so")
+# MDT_LIB_PATH: development A/B of two builds inside one GPU session (default: the in-tree library)
+LIB_PATH = os.environ.get("MDT_LIB_PATH") or os.path.join(_HERE, "libmaskdit_b200.so")
 
 
 class MdtError(RuntimeError):
@@ -96,7 +97,7 @@ def exported_symbols():
 
 
 LAUNCHES = 0  # kernels launched through the C ABI (bench.py reports it as gpu_launches)
-GEMM_PROFILE = None  # when a list: gemm() appends (flops, start_event, end_event) per launch (bench.py roofline)
+GEMM_PROFILE = None  # when a list: gemm() appends (flops, start_event, end_event, shape key) per launch (bench.py roofline)
 
 
 def check(status: int, what: str, n_kernels: int = 1):
@@ -147,7 +148,7 @@ def gemm(A, B, M, N, K, *, lda=None, ldb=None, a_mn=False, b_mn=False, epi=EPI_S
         e0.record()
         check(lib().mdt_gemm_bf16(ctypes.byref(a), stream_ptr()), "mdt_gemm_bf16")
         e1.record()
-        GEMM_PROFILE.append((2.0 * M * N * K, e0, e1))
+        GEMM_PROFILE.append((2.0 * M * N * K, e0, e1, (M, N, K, int(a_mn), int(b_mn), epi, a.out_fp32)))
         return out
     check(lib().mdt_gemm_bf16(ctypes.byref(a), stream_ptr()), "mdt_gemm_bf16")
     return out

@@ -99,45 +99,93 @@ constexpr int kStgFloats = 32 * kStgStride;
 MDT_DEVINL uint2 pack4_bf16(float4 v) { return make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)); }
 MDT_DEVINL float4 unpack4_bf16(uint2 u) { return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y)); }
 
+// Global operands of one chunk (this lane's 4 columns x 8 row groups).  Issue is in order, so the load -> store
+// dependency of a chunk exposes the operand latency once per chunk, and with 2 epilogue warps per scheduler nothing
+// else hides it (r01 in-step timing: the dGELU / gate+residual GEMMs ran at 1025 / 686-1224 TF/s while the
+// operand-free K=4608 dgrad reached 1322).  Two measures: (1) the loads are issued at the top of the chunk, before the
+// accumulator is read and transposed; (2) the operand rows of this warp's NEXT tile are prefetched into L2 a whole
+// tile ahead (cp.async.bulk.prefetch.L2: no destination register, no scoreboard), turning DRAM latency into L2
+// latency.  A register-level software pipeline (refilling row group i with the next chunk's values right after its
+// store) was measured 2x SLOWER on the K=1152 gate+residual GEMM: the in-flight loads share scoreboards with the
+// LDS of the following rows.
+struct EpiCoord {
+  int row_base, nrows, col;  // col = this lane's first column
+  bool valid;                // nrows > 0 && col + 4 <= N
+};
+MDT_DEVINL EpiCoord make_coord(const GemmParams& p, int row_base, int nrows, int col) {
+  return EpiCoord{row_base, nrows, col, nrows > 0 && col + 4 <= p.N};
+}
+
 template <int EPI>
-MDT_DEVINL void epilogue_chunk(const GemmParams& p, uint32_t stg, int row_base, int nrows, int col, int lane) {
-  const int rsub = lane >> 3, c4 = (lane & 7) * 4;
-  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (EPI != EPI_ATOMIC && p.bias) bias4 = ldg128_nc(gaddr(p.bias + col));
-  const size_t row0 = static_cast<size_t>(row_base + rsub);
-  const int osz = (EPI == EPI_ATOMIC || EPI == EPI_GATE_RESID || (EPI == EPI_STORE && p.out_fp32)) ? 4 : 2;
-  uint64_t a_out = gaddr(p.out) + (row0 * p.ldo + col) * osz;
-  uint64_t a_aux = gaddr(p.aux) + (row0 * p.ld_aux + col) * 2;
-  uint64_t a_res = gaddr(p.resid) + (row0 * p.ld_resid + col) * 4;
-  const uint64_t s_out = 4ull * p.ldo * osz, s_aux = 8ull * p.ld_aux, s_res = 16ull * p.ld_resid;
-  const uint32_t sp = stg + (rsub * kStgStride + c4) * 4;
-  // Global operands of the epilogue are fetched for all 8 row groups BEFORE any dependent store is issued: issue is
-  // in order, so a load->store dependency inside the row loop would expose the full global latency 8 times per
-  // chunk (ncu r01: the K=1152 proj GEMM ran at 18 % tensor-pipe activity because of exactly that).
-  float4 res[8];
-  uint2 auxv[8];
-  float4 gate4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  bool gate_uniform = true;
+struct EpiOps {
+  float4 bias4, gate4;
+  bool gate_uniform;
+  float4 res[(EPI == EPI_GATE_RESID || EPI == EPI_STORE) ? 8 : 1];
+  uint2 auxv[EPI == EPI_DGELU ? 8 : 1];
+};
+
+template <int EPI>
+MDT_DEVINL void epi_load(const GemmParams& p, const EpiCoord& c, int lane, EpiOps<EPI>& o) {
+  if (!c.valid) return;
+  const int rsub = lane >> 3;
+  const size_t row0 = static_cast<size_t>(c.row_base + rsub);
+  o.bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (EPI != EPI_ATOMIC && p.bias) o.bias4 = ldg128_nc(gaddr(p.bias + c.col));
   if constexpr (EPI == EPI_GATE_RESID) {
-    const int b0 = row_base / p.rows_per_group, b1 = (row_base + nrows - 1) / p.rows_per_group;
-    gate_uniform = b0 == b1;
-    if (gate_uniform) gate4 = ldg128_nc(gaddr(p.gate + static_cast<size_t>(b0) * p.ld_gate + col));
+    const int b0 = c.row_base / p.rows_per_group, b1 = (c.row_base + c.nrows - 1) / p.rows_per_group;
+    o.gate_uniform = b0 == b1;
+    o.gate4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (o.gate_uniform) o.gate4 = ldg128_nc(gaddr(p.gate + static_cast<size_t>(b0) * p.ld_gate + c.col));
   }
   if constexpr (EPI == EPI_GATE_RESID || EPI == EPI_STORE) {
     if (EPI == EPI_GATE_RESID || p.resid) {
+      const uint64_t a_res = gaddr(p.resid) + (row0 * p.ld_resid + c.col) * 4, s_res = 16ull * p.ld_resid;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (4 * i + rsub < nrows) res[i] = ldg128(a_res + i * s_res);
+        if (4 * i + rsub < c.nrows) o.res[i] = ldg128(a_res + i * s_res);
     }
   }
   if constexpr (EPI == EPI_DGELU) {
+    const uint64_t a_aux = gaddr(p.aux) + (row0 * p.ld_aux + c.col) * 2, s_aux = 8ull * p.ld_aux;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      if (4 * i + rsub < nrows) auxv[i] = ldg64_nc(a_aux + i * s_aux);
+      if (4 * i + rsub < c.nrows) o.auxv[i] = ldg64_nc(a_aux + i * s_aux);
   }
+}
+
+// L2 prefetch of one operand row segment [col0, col0 + ncols) of `row` (a hint: skipped when not 16-byte aligned)
+MDT_DEVINL void prefetch_l2_row(const void* base, size_t row, int ld, int col0, int ncols, int esz) {
+  const uint64_t addr = gaddr(base) + (row * ld + col0) * esz;
+  const uint32_t bytes = static_cast<uint32_t>(ncols * esz) & ~15u;
+  if ((addr & 15) == 0 && bytes)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(addr), "r"(bytes) : "memory");
+}
+template <int EPI>
+MDT_DEVINL void epi_prefetch_tile(const GemmParams& p, int row_base, int nrows, int col_base, int ncols, int lane) {
+  if (lane >= nrows) return;
+  if (col_base + ncols > p.N) ncols = p.N - col_base;
+  if (ncols <= 0) return;
+  const size_t row = static_cast<size_t>(row_base + lane);
+  if constexpr (EPI == EPI_GATE_RESID || EPI == EPI_STORE) {
+    if (EPI == EPI_GATE_RESID || p.resid) prefetch_l2_row(p.resid, row, p.ld_resid, col_base, ncols, 4);
+  }
+  if constexpr (EPI == EPI_DGELU) prefetch_l2_row(p.aux, row, p.ld_aux, col_base, ncols, 2);
+}
+
+// chunk `c` (valid for this lane): transpose-read, fused arithmetic, coalesced stores
+template <int EPI>
+MDT_DEVINL void epilogue_chunk(const GemmParams& p, uint32_t stg, const EpiCoord& c, int lane, const EpiOps<EPI>& o) {
+  const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+  const float4 bias4 = o.bias4;
+  const size_t row0 = static_cast<size_t>(c.row_base + rsub);
+  const int osz = (EPI == EPI_ATOMIC || EPI == EPI_GATE_RESID || (EPI == EPI_STORE && p.out_fp32)) ? 4 : 2;
+  const uint64_t a_out = gaddr(p.out) + (row0 * p.ldo + c.col) * osz;
+  const uint64_t a_aux = gaddr(p.aux) + (row0 * p.ld_aux + c.col) * 2;
+  const uint64_t s_out = 4ull * p.ldo * osz, s_aux = 8ull * p.ld_aux;
+  const uint32_t sp = stg + (rsub * kStgStride + c4) * 4;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    if (4 * i + rsub >= nrows) break;
+    if (4 * i + rsub >= c.nrows) break;
     float4 v = lds128(sp + i * (4 * kStgStride * 4));
     const uint64_t ao = a_out + i * s_out;
     if constexpr (EPI == EPI_ATOMIC) {
@@ -145,7 +193,7 @@ MDT_DEVINL void epilogue_chunk(const GemmParams& p, uint32_t stg, int row_base, 
     } else {
       v.x += bias4.x, v.y += bias4.y, v.z += bias4.z, v.w += bias4.w;
       if constexpr (EPI == EPI_STORE) {
-        if (p.resid) v.x += res[i].x, v.y += res[i].y, v.z += res[i].z, v.w += res[i].w;
+        if (p.resid) v.x += o.res[i].x, v.y += o.res[i].y, v.z += o.res[i].z, v.w += o.res[i].w;
         if (p.act == ACT_SILU) v = make_float4(silu(v.x), silu(v.y), silu(v.z), silu(v.w));
         if (p.out_fp32) stg128(ao, v); else stg64(ao, pack4_bf16(v));
       } else if constexpr (EPI == EPI_GELU) {
@@ -156,15 +204,15 @@ MDT_DEVINL void epilogue_chunk(const GemmParams& p, uint32_t stg, int row_base, 
         stg64(ao, pack4_bf16(make_float4(gelu_tanh(h.x), gelu_tanh(h.y), gelu_tanh(h.z), gelu_tanh(h.w))));
       } else if constexpr (EPI == EPI_GATE_RESID) {
         if (p.aux) stg64(a_aux + i * s_aux, pack4_bf16(v));
-        float4 g = gate4;
-        if (!gate_uniform) {
+        float4 g = o.gate4;
+        if (!o.gate_uniform) {
           const size_t b = (row0 + 4 * i) / p.rows_per_group;
-          g = ldg128_nc(gaddr(p.gate + b * p.ld_gate + col));
+          g = ldg128_nc(gaddr(p.gate + b * p.ld_gate + c.col));
         }
-        const float4 r = res[i];  // may alias `out` (in-place residual update): every element is read before written
+        const float4 r = o.res[i];  // may alias `out` (in-place residual update): each element is read before written
         stg128(ao, make_float4(fmaf(g.x, v.x, r.x), fmaf(g.y, v.y, r.y), fmaf(g.z, v.z, r.z), fmaf(g.w, v.w, r.w)));
       } else if constexpr (EPI == EPI_DGELU) {
-        const float4 h = unpack4_bf16(auxv[i]);
+        const float4 h = unpack4_bf16(o.auxv[i]);
         stg64(ao, pack4_bf16(make_float4(v.x * gelu_tanh_grad(h.x), v.y * gelu_tanh_grad(h.y),
                                          v.z * gelu_tanh_grad(h.z), v.w * gelu_tanh_grad(h.w))));
       }
@@ -213,29 +261,75 @@ __device__ __noinline__ void epilogue_ragged(const GemmParams& p, uint32_t stg, 
   }
 }
 
-// One warp's share of a tile (32 rows x kChunks*32 columns) for ONE epilogue kind.  The chunk loop is deliberately
-// rolled and single-buffered: unrolling / prefetching the next tcgen05.ld was measured SLOWER on B200 (12.3k vs 8.8k
-// cycles per 128x256 bf16 tile, tools/probe_gemm2.py) — the epilogue is instruction-fetch sensitive.
-template <int EPI, int kChunks>
-MDT_DEVINL void epilogue_tile(const GemmParams& p, uint32_t taddr, uint32_t stg, int row_base, int nrows, int col_base,
+// The epilogue warps' whole persistent loop for ONE epilogue kind (one switch per launch: a launch only ever executes
+// the instructions of its own epilogue; ncu v3 showed the epilogue instruction-fetch bound).  The chunk loop is
+// deliberately rolled and the TMEM read single-buffered: unrolling / prefetching the next tcgen05.ld was measured
+// SLOWER on B200 (12.3k vs 8.8k cycles per 128x256 bf16 tile, tools/probe_gemm2.py).
+template <int EPI, int BLOCK_N, int CG>
+MDT_DEVINL void epilogue_loop(const GemmParams& p, UnitSched& sched, uint64_t* tmem_full_bar,
+                              uint64_t* tmem_empty_bar, uint32_t tmem_base, uint32_t stg, int warp, int cta_rank,
                               int lane) {
-#pragma unroll 1
-  for (int ci = 0; ci < kChunks; ++ci) {
-    uint32_t rc[32];
-    tmem_ld_32x32b_x32(taddr + ci * 32, rc);
-    tcgen05_wait_ld();
-    const int col0 = col_base + ci * 32;
-    if (nrows > 0 && col0 < p.N) {  // warp-uniform
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        sts128(stg + (lane * kStgStride + 4 * q) * 4, __uint_as_float(rc[4 * q]), __uint_as_float(rc[4 * q + 1]),
-               __uint_as_float(rc[4 * q + 2]), __uint_as_float(rc[4 * q + 3]));
-      __syncwarp();
-      const int col = col0 + (lane & 7) * 4;
-      if (col + 4 <= p.N) epilogue_chunk<EPI>(p, stg, row_base, nrows, col, lane);
-      else if (col < p.N) epilogue_ragged(p, stg, row_base, nrows, col, lane);
-      __syncwarp();
+  constexpr int TILE_M = BLOCK_M * CG;
+  constexpr int kColsPerWarp = BLOCK_N / 2;  // 128 / 64
+  constexpr int kChunks = kColsPerWarp / 32;
+  constexpr bool kHasOps = EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_GATE_RESID || EPI == EPI_DGELU;
+  const int lane_group = warp & 3;       // tcgen05.ld: warp w may touch TMEM lanes 32*(w%4)..+31
+  const int col_half = (warp - 4) >> 2;  // 0/1
+  const int lcol = (lane & 7) * 4;
+  auto tile_coord = [&](int mt, int nt, int& row_base, int& nrows, int& col_base) {
+    row_base = mt * TILE_M + cta_rank * BLOCK_M + lane_group * 32;
+    nrows = p.M - row_base;
+    nrows = nrows > 32 ? 32 : nrows;
+    col_base = nt * BLOCK_N + col_half * kColsPerWarp;
+  };
+  int as = 0;
+  uint32_t aphase = 0;
+  bool have = sched.next();
+  while (have) {
+    int row_base, nrows, col_base;
+    tile_coord(sched.m_tile(), sched.n_tile(), row_base, nrows, col_base);
+    have = sched.next();
+#ifndef MDT_NO_EPI_PREFETCH
+    if (have && kHasOps) {  // this warp's next tile: operand rows towards L2 while this tile is processed
+      int rb, nr, cb;
+      tile_coord(sched.m_tile(), sched.n_tile(), rb, nr, cb);
+      epi_prefetch_tile<EPI>(p, rb, nr, cb, kColsPerWarp, lane);
     }
+#endif
+    while (!mbar_try_wait(&tmem_full_bar[as], aphase)) {
+    }
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * BLOCK_N +
+                           col_half * kColsPerWarp;
+#pragma unroll 1
+    for (int ci = 0; ci < kChunks; ++ci) {
+      const int col0 = col_base + ci * 32;
+      const EpiCoord c = make_coord(p, row_base, nrows, col0 + lcol);
+      EpiOps<EPI> ops;
+      if constexpr (kHasOps) epi_load<EPI>(p, c, lane, ops);
+      uint32_t rc[32];
+      tmem_ld_32x32b_x32(taddr + ci * 32, rc);
+      tcgen05_wait_ld();
+      if (nrows > 0 && col0 < p.N) {  // warp-uniform
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          sts128(stg + (lane * kStgStride + 4 * q) * 4, __uint_as_float(rc[4 * q]), __uint_as_float(rc[4 * q + 1]),
+                 __uint_as_float(rc[4 * q + 2]), __uint_as_float(rc[4 * q + 3]));
+        __syncwarp();
+        if constexpr (kHasOps || EPI == EPI_ATOMIC) {
+          if (c.valid) epilogue_chunk<EPI>(p, stg, c, lane, ops);
+          else if (c.col < p.N) epilogue_ragged(p, stg, row_base, nrows, c.col, lane);
+        }
+        __syncwarp();
+      }
+    }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (CG == 2) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+      else mbar_arrive(&tmem_empty_bar[as]);
+    }
+    if (++as == 2) as = 0, aphase ^= 1;
   }
 }
 
@@ -372,40 +466,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp >= 4) {
     // ===================== epilogue (every CTA: its own 128 accumulator rows) =====================
-    const int ew = warp - 4;
-    const int lane_group = warp & 3;           // tcgen05.ld: warp w may touch TMEM lanes 32*(w%4)..+31
-    const int col_half = ew >> 2;              // 0/1
-    constexpr int kColsPerWarp = BLOCK_N / 2;  // 128 / 96 / 64
-    int as = 0;
-    uint32_t aphase = 0;
-    while (sched.next()) {
-      const int m0 = sched.m_tile() * TILE_M + cta_rank * BLOCK_M, n0 = sched.n_tile() * BLOCK_N;
-      mbar_wait(&tmem_full_bar[as], aphase);
-      tcgen05_fence_after();
-      const int row_base = m0 + lane_group * 32;
-      int nrows = p.M - row_base;
-      nrows = nrows > 32 ? 32 : nrows;
-      const uint32_t stg = smem_u32(staging) + ew * kStgFloats * 4;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * BLOCK_N +
-                             col_half * kColsPerWarp;
-      const int col_base = n0 + col_half * kColsPerWarp;
-      constexpr int kChunks = kColsPerWarp / 32;
-      switch (p.epi) {  // one switch per tile: a launch only ever executes the instructions of its own epilogue
-        case EPI_STORE: epilogue_tile<EPI_STORE, kChunks>(p, taddr, stg, row_base, nrows, col_base, lane); break;
-        case EPI_GELU: epilogue_tile<EPI_GELU, kChunks>(p, taddr, stg, row_base, nrows, col_base, lane); break;
-        case EPI_GATE_RESID: epilogue_tile<EPI_GATE_RESID, kChunks>(p, taddr, stg, row_base, nrows, col_base, lane); break;
-        case EPI_DGELU: epilogue_tile<EPI_DGELU, kChunks>(p, taddr, stg, row_base, nrows, col_base, lane); break;
-        case EPI_ATOMIC: epilogue_tile<EPI_ATOMIC, kChunks>(p, taddr, stg, row_base, nrows, col_base, lane); break;
-        default: epilogue_tile<99, kChunks>(p, taddr, stg, row_base, nrows, col_base, lane); break;  // debug: no stores
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
-        else mbar_arrive(&tmem_empty_bar[as]);
-      }
-      if (++as == 2) as = 0, aphase ^= 1;
+    const uint32_t stg = smem_u32(staging) + (warp - 4) * kStgFloats * 4;
+#define MDT_EPI_LOOP(E) \
+  epilogue_loop<E, BLOCK_N, CG>(p, sched, tmem_full_bar, tmem_empty_bar, tmem_base, stg, warp, cta_rank, lane)
+    switch (p.epi) {
+      case EPI_STORE: MDT_EPI_LOOP(EPI_STORE); break;
+      case EPI_GELU: MDT_EPI_LOOP(EPI_GELU); break;
+      case EPI_GATE_RESID: MDT_EPI_LOOP(EPI_GATE_RESID); break;
+      case EPI_DGELU: MDT_EPI_LOOP(EPI_DGELU); break;
+      case EPI_ATOMIC: MDT_EPI_LOOP(EPI_ATOMIC); break;
+      default: MDT_EPI_LOOP(99); break;  // debug: accumulators drained, nothing stored
     }
+#undef MDT_EPI_LOOP
   }
 
   __syncwarp();  // role branches above are per-lane; reconverge before the .aligned barriers below

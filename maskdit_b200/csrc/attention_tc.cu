@@ -22,23 +22,34 @@ namespace mdt {
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
+constexpr int fwd_v_offset(int dp, int tk) {
+  const int qk = (kQB + tk) * dp * 2, pb = kQB * tk * 2;
+  return qk > pb ? qk : pb;
+}
+
+// threads per query row: T = 256 splits each row's key columns over two threads (row = tid & 127); for T = 128 one
+// thread per row was measured faster (114 vs 121 us at B=256, d_h=72: the extra barrier costs more than it saves)
+constexpr int fwd_tpr(int tk) { return tk >= 256 ? 2 : 1; }
+
 template <int DP, int TK>
-__global__ void __launch_bounds__(kQB)
+__global__ void __launch_bounds__(kQB * fwd_tpr(TK))
 attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                    int T, int H, int dh, float scale) {
   using TT = TokTile<DP>;
   constexpr int kPBlk = (TK / 8) * 128;                       // bytes per 8-query block of P
   constexpr int kTmemCols = TK;  // O aliases S: S is dead once every row thread has written its P row to smem
   extern __shared__ __align__(128) uint8_t smem[];
-  // P may overwrite Q|K: both are dead once the S MMAs have completed (the row threads only start writing P after
-  // waiting on that commit).  For T = 128 this takes the CTA from 92 KB to 60 KB of smem -> 3 CTAs per SM.
-  constexpr bool kPAlias = kQB * TK * 2 <= (kQB + TK) * DP * 2;
-  const uint32_t sQ = smem_u32(smem), sK = sQ + kQB * DP * 2, sV = sK + TK * DP * 2;
-  const uint32_t sP = kPAlias ? sQ : sV + TK * DP * 2;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (kQB + 2 * TK) * DP * 2 + (kPAlias ? 0 : kQB * TK * 2));
+  // P overwrites Q|K: both are dead once the S MMAs have completed (the row threads only start writing P after
+  // waiting on that commit); V starts behind whichever of the two is larger.  T = 128: 92 KB -> 60 KB of smem (3 CTAs
+  // per SM); T = 256, d_h = 72: 164 KB -> 104 KB (2 CTAs per SM, which is also what the 256 TMEM columns allow).
+  constexpr int kVOff = fwd_v_offset(DP, TK);
+  const uint32_t sQ = smem_u32(smem), sK = sQ + kQB * DP * 2, sV = sQ + kVOff;
+  const uint32_t sP = sQ;
+  float* s_red = reinterpret_cast<float*>(smem + kVOff + TK * DP * 2);  // [2][128] row max, [2][128] row sum
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + 4 * kQB);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kQB - 1), half = tid >> 7;
   const int b = blockIdx.y / H, h = blockIdx.y % H, q0 = blockIdx.x * kQB;
   const long long rs = 3LL * H * dh;
   const __nv_bfloat16* base = qkv + static_cast<long long>(b) * T * rs;
@@ -64,23 +75,30 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
   mbar_wait(bar, 0);
   tcgen05_fence_after();
 
-  // softmax of this thread's row, straight out of TMEM (lane = row)
-  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  // softmax of this thread's half row, straight out of TMEM (lane = row)
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const float sl = scale * 1.4426950408889634f;
+  constexpr int kTPR = fwd_tpr(TK), kHalf = TK / kTPR;
+  const int c_lo = half * kHalf;
   float m = -INFINITY;
 #pragma unroll 1
-  for (int c = 0; c < TK; c += 32) {
+  for (int c = c_lo; c < c_lo + kHalf; c += 32) {
     uint32_t r[32];
     tmem_ld_32x32b_x32(tS + lane_addr + c, r);
     tcgen05_wait_ld();
 #pragma unroll
     for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
   }
+  if constexpr (kTPR == 2) {
+    s_red[half * kQB + row] = m;
+    __syncthreads();
+    m = fmaxf(s_red[row], s_red[kQB + row]);
+  }
   const float msl = m * sl;
   float l = 0.f;
-  const uint32_t prow = sP + (tid >> 3) * kPBlk + (tid & 7) * 16;
+  const uint32_t prow = sP + (row >> 3) * kPBlk + (row & 7) * 16;
 #pragma unroll 1
-  for (int c = 0; c < TK; c += 32) {
+  for (int c = c_lo; c < c_lo + kHalf; c += 32) {
     uint32_t r[32];
     tmem_ld_32x32b_x32(tS + lane_addr + c, r);
     tcgen05_wait_ld();
@@ -96,6 +114,7 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
               make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7])));
     }
   }
+  if constexpr (kTPR == 2) s_red[(2 + half) * kQB + row] = l;
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
@@ -109,17 +128,19 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
                 make_smem_desc_nosw(sV + k * 2 * TT::ROWBLK, TT::ROWBLK, 128), idesc, k > 0 ? 1u : 0u);
     umma_commit(bar);
   }
+  if constexpr (kTPR == 2) l = s_red[2 * kQB + row] + s_red[3 * kQB + row];
+  const float inv_l = 1.f / l;
+  const int q = q0 + row;
+  __nv_bfloat16* orow = out + (static_cast<long long>(b) * T + q) * (H * dh) + h * dh;
+  if (lse && half == 0) lse[(static_cast<long long>(b) * H + h) * T + q] = m * scale + logf(l);
   mbar_wait(bar, 1);
   tcgen05_fence_after();
-  const float inv_l = 1.f / l;
-  const int q = q0 + tid;
-  __nv_bfloat16* orow = out + (static_cast<long long>(b) * T + q) * (H * dh) + h * dh;
   {
-    uint32_t r[DP];
-    tmem_ld_cols<DP>(tO + lane_addr, r);
-    store_row_bf16<DP>(orow, 0, r, dh, inv_l);
+    constexpr int HC = DP / kTPR;
+    uint32_t r[HC];
+    tmem_ld_cols<HC>(tO + lane_addr + half * HC, r);
+    store_row_bf16<HC>(orow, half * HC, r, dh, inv_l);
   }
-  if (lse) lse[(static_cast<long long>(b) * H + h) * T + q] = m * scale + logf(l);
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -359,15 +380,14 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 template <int DP, int TK>
 static int launch_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale,
                       cudaStream_t st) {
-  constexpr bool kPAlias = kQB * TK * 2 <= (kQB + TK) * DP * 2;
-  const int smem = (kQB + 2 * TK) * DP * 2 + (kPAlias ? 0 : kQB * TK * 2) + 64;
+  const int smem = fwd_v_offset(DP, TK) + TK * DP * 2 + 4 * kQB * 4 + 64;
   auto kern = attn_tc_fwd_kernel<DP, TK>;
   static bool set = false;
   if (!set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return MDT_ERR_CUDA;
     set = true;
   }
-  kern<<<dim3(T / kQB, B * H), kQB, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv),
+  kern<<<dim3(T / kQB, B * H), kQB * fwd_tpr(TK), smem, st>>>(static_cast<const __nv_bfloat16*>(qkv),
                                                  static_cast<__nv_bfloat16*>(out), lse, T, H, dh, scale);
   return cudaGetLastError() == cudaSuccess ? MDT_OK : MDT_ERR_CUDA;
 }

@@ -99,15 +99,16 @@ constexpr int kStgFloats = 32 * kStgStride;
 MDT_DEVINL uint2 pack4_bf16(float4 v) { return make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)); }
 MDT_DEVINL float4 unpack4_bf16(uint2 u) { return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y)); }
 
-// Global operands of one chunk (this lane's 4 columns x 8 row groups).  Issue is in order, so the load -> store
-// dependency of a chunk exposes the operand latency once per chunk, and with 2 epilogue warps per scheduler nothing
-// else hides it (r01 in-step timing: the dGELU / gate+residual GEMMs ran at 1025 / 686-1224 TF/s while the
-// operand-free K=4608 dgrad reached 1322).  Two measures: (1) the loads are issued at the top of the chunk, before the
-// accumulator is read and transposed; (2) the operand rows of this warp's NEXT tile are prefetched into L2 a whole
-// tile ahead (cp.async.bulk.prefetch.L2: no destination register, no scoreboard), turning DRAM latency into L2
-// latency.  A register-level software pipeline (refilling row group i with the next chunk's values right after its
-// store) was measured 2x SLOWER on the K=1152 gate+residual GEMM: the in-flight loads share scoreboards with the
-// LDS of the following rows.
+// Global operands of one chunk (this lane's 4 columns x 8 row groups) are fetched for all 8 row groups BEFORE any
+// dependent store is issued: issue is in order, so a load -> store dependency inside the row loop would expose the
+// full global latency 8 times per chunk (ncu r01: the K=1152 proj GEMM ran at 18 % tensor-pipe activity because of
+// exactly that).  Measured and rejected on top of this (A/B on one box, in-step timing, tools/gemm_shapes_step.py):
+//   - a register-level software pipeline (row group i refilled with the next chunk's values right after its store):
+//     2x SLOWER on the K=1152 gate+residual GEMM - the in-flight loads share scoreboards with the following LDS;
+//   - cp.async.bulk.prefetch.L2 of the next tile's operand rows: 3-4 % slower on the dGELU / gate+residual GEMMs;
+//   - issuing the chunk's loads above the tcgen05.ld (as done now): neutral.
+// The operand latency is therefore not what separates these epilogues (1000-1200 TF/s in-step) from the operand-free
+// ones (1250-1390): it is their instruction count on two warps per scheduler.
 struct EpiCoord {
   int row_base, nrows, col;  // col = this lane's first column
   bool valid;                // nrows > 0 && col + 4 <= N
@@ -151,25 +152,6 @@ MDT_DEVINL void epi_load(const GemmParams& p, const EpiCoord& c, int lane, EpiOp
     for (int i = 0; i < 8; ++i)
       if (4 * i + rsub < c.nrows) o.auxv[i] = ldg64_nc(a_aux + i * s_aux);
   }
-}
-
-// L2 prefetch of one operand row segment [col0, col0 + ncols) of `row` (a hint: skipped when not 16-byte aligned)
-MDT_DEVINL void prefetch_l2_row(const void* base, size_t row, int ld, int col0, int ncols, int esz) {
-  const uint64_t addr = gaddr(base) + (row * ld + col0) * esz;
-  const uint32_t bytes = static_cast<uint32_t>(ncols * esz) & ~15u;
-  if ((addr & 15) == 0 && bytes)
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(addr), "r"(bytes) : "memory");
-}
-template <int EPI>
-MDT_DEVINL void epi_prefetch_tile(const GemmParams& p, int row_base, int nrows, int col_base, int ncols, int lane) {
-  if (lane >= nrows) return;
-  if (col_base + ncols > p.N) ncols = p.N - col_base;
-  if (ncols <= 0) return;
-  const size_t row = static_cast<size_t>(row_base + lane);
-  if constexpr (EPI == EPI_GATE_RESID || EPI == EPI_STORE) {
-    if (EPI == EPI_GATE_RESID || p.resid) prefetch_l2_row(p.resid, row, p.ld_resid, col_base, ncols, 4);
-  }
-  if constexpr (EPI == EPI_DGELU) prefetch_l2_row(p.aux, row, p.ld_aux, col_base, ncols, 2);
 }
 
 // chunk `c` (valid for this lane): transpose-read, fused arithmetic, coalesced stores
@@ -289,13 +271,6 @@ MDT_DEVINL void epilogue_loop(const GemmParams& p, UnitSched& sched, uint64_t* t
     int row_base, nrows, col_base;
     tile_coord(sched.m_tile(), sched.n_tile(), row_base, nrows, col_base);
     have = sched.next();
-#ifndef MDT_NO_EPI_PREFETCH
-    if (have && kHasOps) {  // this warp's next tile: operand rows towards L2 while this tile is processed
-      int rb, nr, cb;
-      tile_coord(sched.m_tile(), sched.n_tile(), rb, nr, cb);
-      epi_prefetch_tile<EPI>(p, rb, nr, cb, kColsPerWarp, lane);
-    }
-#endif
     while (!mbar_try_wait(&tmem_full_bar[as], aphase)) {
     }
     tcgen05_fence_after();

@@ -122,6 +122,15 @@ int mdt_ln_modulate_bwd(const void* dxmod_bf16, const float* x, const float* mea
 int mdt_gate_bwd(const float* g, const void* y_bf16, const float* gate, int ld_gate, int rows_per_group,
                  void* dy_bf16, float* dgate, int ld_dgate, float* dbias, int M, int D, void* stream);
 
+/* mdt_ln_modulate_bwd immediately followed by mdt_gate_bwd on the finished residual gradient g, in one pass
+ * (the block backward alternates exactly these two: models/maskdit.py:190-191 differentiated right to left).
+ * y_bf16 == NULL: LN backward only.  Same arguments and arithmetic as the two separate entry points.          */
+int mdt_ln_modulate_bwd_gate(const void* dxmod_bf16, const float* x, const float* mean, const float* rstd,
+                             const float* scale, int ld_mod, int rows_per_group, float* g, int accumulate,
+                             float* dshift, float* dscale, int ld_dmod, const void* y_bf16, const float* gate,
+                             int ld_gate, void* dy_bf16, float* dgate, int ld_dgate, float* dbias, int M, int D,
+                             void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Multi-head attention core of timm Attention (ctor models/maskdit.py:178):
  *   qkv [B,T,3,H,dh] bf16 -> out [B,T,H*dh] bf16 = softmax(q k^T / sqrt(dh)) v ; lse [B,H,T] f32 (log-sum-exp)

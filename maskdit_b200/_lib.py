@@ -57,6 +57,7 @@ _SIGS = {
     "mdt_ln_modulate": [_P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _F, _P],
     "mdt_ln_modulate_bwd": [_P, _P, _P, _P, _P, _I, _I, _P, _I, _P, _P, _I, _I, _I, _P],
     "mdt_gate_bwd": [_P, _P, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P],
+    "mdt_ln_modulate_bwd_gate": [_P, _P, _P, _P, _P, _I, _I, _P, _I, _P, _P, _I, _P, _P, _I, _P, _P, _I, _P, _I, _I, _P],
     "mdt_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _P],
     "mdt_attention_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mdt_unmask_tokens": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

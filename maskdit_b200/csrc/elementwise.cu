@@ -382,6 +382,112 @@ __global__ void gate_bwd_kernel(const float* __restrict__ g, const __nv_bfloat16
 }
 
 // =========================================================================================================
+// LN-modulate backward FUSED with the gate backward that consumes its result.  In the block backward every LN
+// backward (which finishes the residual-stream gradient g) is followed by the gate backward of the next branch, which
+// re-reads all of g: fusing the two removes that 4 B/element read and a launch (22 -> 18 B/element for the pair).
+// Column-owner layout (thread = 4 adjacent columns, block = D/4 threads x rows_per_block rows of one sample): the
+// per-column reductions (dshift, dscale, dgate, dbias) stay in 16 registers; the two per-row LN statistics are
+// block-reduced for 4 rows at a time (warp shuffles + one __syncthreads per batch, smem double-buffered by parity).
+// =========================================================================================================
+constexpr int kLgBatch = 4;
+constexpr int kLgMaxThreads = 320;  // D <= 1280
+template <bool GATE>
+__global__ void __launch_bounds__(kLgMaxThreads, 2)
+ln_bwd_gate_kernel(const __nv_bfloat16* __restrict__ dxmod, const float* __restrict__ x,
+                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
+                   int ld_mod, int rows_per_group, float* __restrict__ g, int accumulate, float* __restrict__ dshift,
+                   float* __restrict__ dscale, int ld_dmod, const __nv_bfloat16* __restrict__ y,
+                   const float* __restrict__ gate, int ld_gate, __nv_bfloat16* __restrict__ dy,
+                   float* __restrict__ dgate, int ld_dgate, float* __restrict__ dbias, int M, int D,
+                   int rows_per_block) {
+  __shared__ float4 s_part[2][kLgMaxThreads / 32][2];  // [parity][warp][{s1 x4}, {s2 x4}]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int c = tid * 4;
+  const int row0 = blockIdx.x * rows_per_block;
+  const int r_end = min(M, row0 + rows_per_block);
+  const int b = row0 / rows_per_group;
+  const float inv_d = 1.f / D;
+  float4 sc1 = ldg128_nc(gaddr(scale + static_cast<size_t>(b) * ld_mod + c));
+  sc1.x += 1.f, sc1.y += 1.f, sc1.z += 1.f, sc1.w += 1.f;
+  float4 gt = make_float4(0, 0, 0, 0);
+  if (GATE) gt = ldg128_nc(gaddr(gate + static_cast<size_t>(b) * ld_gate + c));
+  float4 a_sh = make_float4(0, 0, 0, 0), a_sc = a_sh, ag = a_sh, ab = a_sh;
+  int parity = 0;
+  for (int r = row0; r < r_end; r += kLgBatch, parity ^= 1) {
+    uint2 dv[kLgBatch], yv[kLgBatch];
+    float4 xv[kLgBatch], gv[kLgBatch];
+    float mu[kLgBatch], rs[kLgBatch];
+#pragma unroll
+    for (int j = 0; j < kLgBatch; ++j) {
+      const bool ok = r + j < r_end;
+      const size_t e = static_cast<size_t>(r + j) * D + c;
+      dv[j] = ok ? ldg64_nc(gaddr(dxmod + e)) : make_uint2(0, 0);
+      xv[j] = ok ? ldg128_nc(gaddr(x + e)) : make_float4(0, 0, 0, 0);
+      gv[j] = (ok && accumulate) ? ldg128(gaddr(g + e)) : make_float4(0, 0, 0, 0);
+      if (GATE) yv[j] = ok ? ldg64_nc(gaddr(y + e)) : make_uint2(0, 0);
+      mu[j] = ok ? mean[r + j] : 0.f;
+      rs[j] = ok ? rstd[r + j] : 0.f;
+    }
+    float s1[kLgBatch], s2[kLgBatch];
+#pragma unroll
+    for (int j = 0; j < kLgBatch; ++j) {
+      const float4 d = make_float4(bf16_lo(dv[j].x), bf16_hi(dv[j].x), bf16_lo(dv[j].y), bf16_hi(dv[j].y));
+      const float4 xh = make_float4((xv[j].x - mu[j]) * rs[j], (xv[j].y - mu[j]) * rs[j], (xv[j].z - mu[j]) * rs[j],
+                                    (xv[j].w - mu[j]) * rs[j]);
+      xv[j] = xh;
+      a_sh.x += d.x, a_sh.y += d.y, a_sh.z += d.z, a_sh.w += d.w;
+      a_sc.x = fmaf(d.x, xh.x, a_sc.x), a_sc.y = fmaf(d.y, xh.y, a_sc.y);
+      a_sc.z = fmaf(d.z, xh.z, a_sc.z), a_sc.w = fmaf(d.w, xh.w, a_sc.w);
+      const float4 t = make_float4(d.x * sc1.x, d.y * sc1.y, d.z * sc1.z, d.w * sc1.w);
+      s1[j] = (t.x + t.y) + (t.z + t.w);
+      s2[j] = (t.x * xh.x + t.y * xh.y) + (t.z * xh.z + t.w * xh.w);
+    }
+#pragma unroll
+    for (int j = 0; j < kLgBatch; ++j) s1[j] = warp_sum(s1[j]), s2[j] = warp_sum(s2[j]);
+    if (lane == 0) {
+      s_part[parity][warp][0] = make_float4(s1[0], s1[1], s1[2], s1[3]);
+      s_part[parity][warp][1] = make_float4(s2[0], s2[1], s2[2], s2[3]);
+    }
+    __syncthreads();
+    float4 t1 = make_float4(0, 0, 0, 0), t2 = t1;
+    for (int w = 0; w < nwarps; ++w) {
+      const float4 p1 = s_part[parity][w][0], p2 = s_part[parity][w][1];
+      t1.x += p1.x, t1.y += p1.y, t1.z += p1.z, t1.w += p1.w;
+      t2.x += p2.x, t2.y += p2.y, t2.z += p2.z, t2.w += p2.w;
+    }
+    s1[0] = t1.x, s1[1] = t1.y, s1[2] = t1.z, s1[3] = t1.w;
+    s2[0] = t2.x, s2[1] = t2.y, s2[2] = t2.z, s2[3] = t2.w;
+#pragma unroll
+    for (int j = 0; j < kLgBatch; ++j) {
+      if (r + j >= r_end) break;
+      const size_t e = static_cast<size_t>(r + j) * D + c;
+      const float m1 = s1[j] * inv_d, m2 = s2[j] * inv_d;
+      const float4 d = make_float4(bf16_lo(dv[j].x), bf16_hi(dv[j].x), bf16_lo(dv[j].y), bf16_hi(dv[j].y));
+      const float4 xh = xv[j];
+      float4 o;
+      o.x = fmaf(rs[j], d.x * sc1.x - m1 - xh.x * m2, gv[j].x);
+      o.y = fmaf(rs[j], d.y * sc1.y - m1 - xh.y * m2, gv[j].y);
+      o.z = fmaf(rs[j], d.z * sc1.z - m1 - xh.z * m2, gv[j].z);
+      o.w = fmaf(rs[j], d.w * sc1.w - m1 - xh.w * m2, gv[j].w);
+      stg128(gaddr(g + e), o);
+      if (GATE) {
+        const float4 q = make_float4(o.x * gt.x, o.y * gt.y, o.z * gt.z, o.w * gt.w);
+        stg64(gaddr(dy + e), make_uint2(pack_bf16(q.x, q.y), pack_bf16(q.z, q.w)));
+        ag.x = fmaf(o.x, bf16_lo(yv[j].x), ag.x), ag.y = fmaf(o.y, bf16_hi(yv[j].x), ag.y);
+        ag.z = fmaf(o.z, bf16_lo(yv[j].y), ag.z), ag.w = fmaf(o.w, bf16_hi(yv[j].y), ag.w);
+        ab.x += q.x, ab.y += q.y, ab.z += q.z, ab.w += q.w;
+      }
+    }
+  }
+  red_add_v4(gaddr(dshift + static_cast<size_t>(b) * ld_dmod + c), a_sh);
+  red_add_v4(gaddr(dscale + static_cast<size_t>(b) * ld_dmod + c), a_sc);
+  if (GATE) {
+    red_add_v4(gaddr(dgate + static_cast<size_t>(b) * ld_dgate + c), ag);
+    if (dbias) red_add_v4(gaddr(dbias + c), ab);
+  }
+}
+
+// =========================================================================================================
 // unmask_tokens (+ decoder_pos_embed) and its backward.  Thread owns 4 columns; block = D/4 threads x 16 positions.
 // =========================================================================================================
 constexpr int kUmPos = 16;
@@ -556,6 +662,34 @@ int mdt_gate_bwd(const float* g, const void* y_bf16, const float* gate, int ld_g
   gate_bwd_kernel<<<M / rpb, threads, 0, S(stream)>>>(g, static_cast<const __nv_bfloat16*>(y_bf16), gate, ld_gate,
                                                       rows_per_group, static_cast<__nv_bfloat16*>(dy_bf16), dgate,
                                                       ld_dgate, dbias, M, D, rpb);
+  return launch_status();
+}
+
+// LN-modulate backward + the gate backward of the branch that consumes the finished residual gradient (y == NULL:
+// plain LN backward).  Same arithmetic as mdt_ln_modulate_bwd followed by mdt_gate_bwd.
+int mdt_ln_modulate_bwd_gate(const void* dxmod_bf16, const float* x, const float* mean, const float* rstd,
+                             const float* scale, int ld_mod, int rows_per_group, float* g, int accumulate,
+                             float* dshift, float* dscale, int ld_dmod, const void* y_bf16, const float* gate,
+                             int ld_gate, void* dy_bf16, float* dgate, int ld_dgate, float* dbias, int M, int D,
+                             void* stream) {
+  if (!dxmod_bf16 || !x || !mean || !rstd || !scale || !g || !dshift || !dscale || M <= 0) return MDT_ERR_ARG;
+  if (rows_per_group <= 0 || M % rows_per_group || (ld_mod & 3) || (ld_dmod & 3)) return MDT_ERR_ARG;
+  if (y_bf16 && (!gate || !dy_bf16 || !dgate || (ld_gate & 3) || (ld_dgate & 3))) return MDT_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(dshift) | reinterpret_cast<uintptr_t>(dscale) |
+       reinterpret_cast<uintptr_t>(gate) | reinterpret_cast<uintptr_t>(dgate) | reinterpret_cast<uintptr_t>(dbias)) & 15)
+    return MDT_ERR_ARG;
+  if (D % 128 || D / 4 > kLgMaxThreads) return MDT_ERR_UNSUPPORTED;  // D <= 1280, as the LN kernels
+  const int rpb = gcd_int(rows_per_group, 32);
+  const int grid = M / rpb;
+  if (y_bf16)
+    ln_bwd_gate_kernel<true><<<grid, D / 4, 0, S(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dxmod_bf16), x, mean, rstd, scale, ld_mod, rows_per_group, g, accumulate,
+        dshift, dscale, ld_dmod, static_cast<const __nv_bfloat16*>(y_bf16), gate, ld_gate,
+        static_cast<__nv_bfloat16*>(dy_bf16), dgate, ld_dgate, dbias, M, D, rpb);
+  else
+    ln_bwd_gate_kernel<false><<<grid, D / 4, 0, S(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dxmod_bf16), x, mean, rstd, scale, ld_mod, rows_per_group, g, accumulate,
+        dshift, dscale, ld_dmod, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, M, D, rpb);
   return launch_status();
 }
 

@@ -195,11 +195,15 @@ class Engine:
         dxf = torch.empty(Md, Dd, dtype=bf16, device=dev)
         gemm(dF16, self.w16("model.final_layer.linear.weight"), Md, Dd, pd, b_mn=True, out=dxf)
         Gz = torch.empty(Md, Dd, dtype=f32, device=dev)
-        ops.ln_modulate_bwd(dxf, ctx["Z_out"], ctx["mean_f"], ctx["rstd_f"], mod[:, o + Dd:], NA, L, Gz, False,
-                            dmod[:, o:], dmod[:, o + Dd:], NA, Md, Dd)
+        # every LN backward finishes the residual-stream gradient that the NEXT gate backward consumes: one fused pass
+        dec, dec_sv = list(reversed(self.dec)), list(reversed(ctx["dec"]))
+        dy2 = ops.ln_modulate_bwd_gate(dxf, ctx["Z_out"], ctx["mean_f"], ctx["rstd_f"], mod[:, o + Dd:], NA, L, Gz,
+                                       False, dmod[:, o:], dmod[:, o + Dd:], NA, Md, Dd,
+                                       gate_next=self._mlp_gate(dec[0], dec_sv[0], mod, dmod) if dec else None)
         # ---- decoder blocks
-        for spec, saved in zip(reversed(self.dec), reversed(ctx["dec"])):
-            self._block_bwd(spec, saved, Gz, mod, dmod, B, L)
+        for i, (spec, saved) in enumerate(zip(dec, dec_sv)):
+            nxt = self._mlp_gate(dec[i + 1], dec_sv[i + 1], mod, dmod) if i + 1 < len(dec) else None
+            dy2 = self._block_bwd(spec, saved, Gz, mod, dmod, B, L, dy2, nxt)
             if on_ready is not None:
                 on_ready(*st.prefix_range(spec.prefix + "."))
         # ---- unmask + decoder layer
@@ -213,11 +217,14 @@ class Engine:
         dxmd = torch.empty(Me, D, dtype=bf16, device=dev)
         gemm(du, self.w16("model.decoder_layer.linear.weight"), Me, D, Dd, b_mn=True, out=dxmd)
         Ge = torch.empty(Me, D, dtype=f32, device=dev)
-        ops.ln_modulate_bwd(dxmd, ctx["X_enc"], ctx["mean_d"], ctx["rstd_d"], mod[:, o + D:], NA, T, Ge, False,
-                            dmod[:, o:], dmod[:, o + D:], NA, Me, D)
+        enc, enc_sv = list(reversed(self.enc)), list(reversed(ctx["enc"]))
+        dy2 = ops.ln_modulate_bwd_gate(dxmd, ctx["X_enc"], ctx["mean_d"], ctx["rstd_d"], mod[:, o + D:], NA, T, Ge,
+                                       False, dmod[:, o:], dmod[:, o + D:], NA, Me, D,
+                                       gate_next=self._mlp_gate(enc[0], enc_sv[0], mod, dmod) if enc else None)
         # ---- encoder blocks
-        for spec, saved in zip(reversed(self.enc), reversed(ctx["enc"])):
-            self._block_bwd(spec, saved, Ge, mod, dmod, B, T)
+        for i, (spec, saved) in enumerate(zip(enc, enc_sv)):
+            nxt = self._mlp_gate(enc[i + 1], enc_sv[i + 1], mod, dmod) if i + 1 < len(enc) else None
+            dy2 = self._block_bwd(spec, saved, Ge, mod, dmod, B, T, dy2, nxt)
             if on_ready is not None:
                 on_ready(*st.prefix_range(spec.prefix + "."))
         # ---- patch embedding (no input gradient needed)
@@ -257,15 +264,25 @@ class Engine:
         """gout[n_out, k_in] += dY[tokens, n_out]^T @ Xin[tokens, k_in]   (stream-K, fp32 red.add)"""
         gemm(dY, Xin, n_out, k_in, tokens, a_mn=True, b_mn=True, out=gout, ldo=k_in, epi=EPI_ATOMIC)
 
-    def _block_bwd(self, s: BlockSpec, sv, Gr, mod, dmod, B, T):
-        """Backward of one DiTBlock; Gr [M, D] f32 is the residual-stream gradient, updated in place."""
+    def _mlp_gate(self, s: BlockSpec, sv, mod, dmod):
+        """Arguments of the MLP-branch gate backward of block `s` (consumed by ops.ln_modulate_bwd_gate)."""
+        o, D = s.mod_off, s.dim
+        return (sv["y2"], mod[:, o + 5 * D:], self.NA, dmod[:, o + 5 * D:], self.NA,
+                self.store.gview(f"{s.prefix}.mlp.fc2.bias"))
+
+    def _block_bwd(self, s: BlockSpec, sv, Gr, mod, dmod, B, T, dy2=None, gate_next=None):
+        """Backward of one DiTBlock; Gr [M, D] f32 is the residual-stream gradient, updated in place.
+        `dy2` = gradient of this block's MLP-branch output when the caller's LN backward already produced it (fused
+        gate backward); `gate_next` = the MLP gate of the block processed next, fused into this block's last LN
+        backward, whose dy is returned."""
         D, M, NA, o, p = s.dim, B * T, self.NA, s.mod_off, s.prefix
         G = self.store.gview
         dev = Gr.device
         H4 = sv["a"].shape[1]
         # x2 = x1 + gate_mlp * (fc2(gelu(fc1(xm2))))
-        dy2 = ops.gate_bwd(Gr, sv["y2"], mod[:, o + 5 * D:], NA, T, dmod[:, o + 5 * D:], NA, G(f"{p}.mlp.fc2.bias"),
-                           M, D)
+        if dy2 is None:
+            dy2 = ops.gate_bwd(Gr, sv["y2"], mod[:, o + 5 * D:], NA, T, dmod[:, o + 5 * D:], NA,
+                               G(f"{p}.mlp.fc2.bias"), M, D)
         dh = torch.empty(M, H4, dtype=bf16, device=dev)
         gemm(dy2, self.w16(f"{p}.mlp.fc2.weight"), M, H4, D, b_mn=True, out=dh, epi=EPI_DGELU, aux=sv["hpre"],
              ld_aux=H4)
@@ -276,11 +293,11 @@ class Engine:
         gemm(dh, self.w16(f"{p}.mlp.fc1.weight"), M, D, H4, b_mn=True, out=dxm2)
         self._wgrad(dh, sv["xm2"], H4, D, M, G(f"{p}.mlp.fc1.weight"))
         del dh
-        ops.ln_modulate_bwd(dxm2, sv["X1"], sv["mean2"], sv["rstd2"], mod[:, o + 4 * D:], NA, T, Gr, True,
-                            dmod[:, o + 3 * D:], dmod[:, o + 4 * D:], NA, M, D)
-        # x1 = x + gate_msa * proj(attn(qkv(xm1)))
-        dy1 = ops.gate_bwd(Gr, sv["y1"], mod[:, o + 2 * D:], NA, T, dmod[:, o + 2 * D:], NA, G(f"{p}.attn.proj.bias"),
-                           M, D)
+        # x1 = x + gate_msa * proj(attn(qkv(xm1))): its gate backward rides on the LN2 backward
+        dy1 = ops.ln_modulate_bwd_gate(dxm2, sv["X1"], sv["mean2"], sv["rstd2"], mod[:, o + 4 * D:], NA, T, Gr, True,
+                                       dmod[:, o + 3 * D:], dmod[:, o + 4 * D:], NA, M, D,
+                                       gate_next=(sv["y1"], mod[:, o + 2 * D:], NA, dmod[:, o + 2 * D:], NA,
+                                                  G(f"{p}.attn.proj.bias")))
         dO = torch.empty(M, D, dtype=bf16, device=dev)
         gemm(dy1, self.w16(f"{p}.attn.proj.weight"), M, D, D, b_mn=True, out=dO)
         self._wgrad(dy1, sv["O"], D, D, M, G(f"{p}.attn.proj.weight"))
@@ -290,5 +307,5 @@ class Engine:
         dxm1 = torch.empty(M, D, dtype=bf16, device=dev)
         gemm(dqkv, self.w16(f"{p}.attn.qkv.weight"), M, D, 3 * D, b_mn=True, out=dxm1)
         self._wgrad(dqkv, sv["xm1"], 3 * D, D, M, G(f"{p}.attn.qkv.weight"))
-        ops.ln_modulate_bwd(dxm1, sv["X"], sv["mean1"], sv["rstd1"], mod[:, o + D:], NA, T, Gr, True, dmod[:, o:],
-                            dmod[:, o + D:], NA, M, D)
+        return ops.ln_modulate_bwd_gate(dxm1, sv["X"], sv["mean1"], sv["rstd1"], mod[:, o + D:], NA, T, Gr, True,
+                                        dmod[:, o:], dmod[:, o + D:], NA, M, D, gate_next=gate_next)

@@ -107,6 +107,23 @@ def ln_modulate_bwd(dxmod, x, mean, rstd, scale, ld_mod, rows_per_group, g, accu
           "mdt_ln_modulate_bwd")
 
 
+def ln_modulate_bwd_gate(dxmod, x, mean, rstd, scale, ld_mod, rows_per_group, g, accumulate, dshift, dscale, ld_dmod,
+                         M, D, gate_next=None):
+    """LN-modulate backward; with `gate_next = (y, gate, ld_gate, dgate, ld_dgate, dbias)` also the gate backward of
+    the branch that consumes the finished residual gradient (one pass over g).  Returns dy (bf16) or None."""
+    dy = None
+    y = gate = dgate = dbias = None
+    ld_gate = ld_dgate = 0
+    if gate_next is not None:
+        y, gate, ld_gate, dgate, ld_dgate, dbias = gate_next
+        dy = torch.empty(M, D, dtype=bf16, device=g.device)
+    check(lib().mdt_ln_modulate_bwd_gate(ptr(dxmod), ptr(x), ptr(mean), ptr(rstd), ptr(scale), ld_mod, rows_per_group,
+                                         ptr(g), int(accumulate), ptr(dshift), ptr(dscale), ld_dmod, ptr(y), ptr(gate),
+                                         ld_gate, ptr(dy), ptr(dgate), ld_dgate, ptr(dbias), M, D, stream_ptr()),
+          "mdt_ln_modulate_bwd_gate")
+    return dy
+
+
 def gate_bwd(g, y, gate, ld_gate, rows_per_group, dgate, ld_dgate, dbias, M, D):
     dy = torch.empty(M, D, dtype=bf16, device=g.device)
     check(lib().mdt_gate_bwd(ptr(g), ptr(y), ptr(gate), ld_gate, rows_per_group, ptr(dy), ptr(dgate), ld_dgate,

@@ -210,6 +210,46 @@ def test_ln_modulate_fwd_bwd(ops, D, T, B):
     close(g2, xr.grad, 1e-3, "ln bwd dx (init)")
 
 
+@pytest.mark.parametrize("D,T,B,fused_gate", [(1152, 128, 4, True), (512, 16, 2, True), (1152, 128, 2, False),
+                                              (512, 256, 3, True), (1280, 8, 2, True), (384, 20, 2, True)])
+def test_ln_modulate_bwd_gate(ops, D, T, B, fused_gate):
+    """Fused LN-modulate backward + gate backward == the two separate kernels == autograd."""
+    torch.manual_seed(16)
+    M = B * T
+    x = torch.randn(M, D, device=dev()) * 2 + 0.3
+    mod = torch.randn(B, 3 * D, device=dev()) * 0.5
+    shift, scale, gate = mod[:, :D], mod[:, D:2 * D], mod[:, 2 * D:]
+    _, mean, rstd = ops.ln_modulate(x, shift, scale, 3 * D, T, M, D)
+    dxmod, y = rb(M, D), rb(M, D)
+    g0 = torch.randn(M, D, device=dev())
+    # separate kernels
+    g_a, dmod_a, dbias_a = g0.clone(), torch.zeros(B, 3 * D, device=dev()), torch.zeros(D, device=dev())
+    ops.ln_modulate_bwd(dxmod, x, mean, rstd, scale, 3 * D, T, g_a, True, dmod_a[:, :D], dmod_a[:, D:], 3 * D, M, D)
+    dy_a = ops.gate_bwd(g_a, y, gate, 3 * D, T, dmod_a[:, 2 * D:], 3 * D, dbias_a, M, D)
+    # fused
+    g_b, dmod_b, dbias_b = g0.clone(), torch.zeros(B, 3 * D, device=dev()), torch.zeros(D, device=dev())
+    gn = (y, gate, 3 * D, dmod_b[:, 2 * D:], 3 * D, dbias_b) if fused_gate else None
+    dy_b = ops.ln_modulate_bwd_gate(dxmod, x, mean, rstd, scale, 3 * D, T, g_b, True, dmod_b[:, :D], dmod_b[:, D:],
+                                    3 * D, M, D, gate_next=gn)
+    close(g_b, g_a, 1e-5, "fused g")
+    close(dmod_b[:, :2 * D], dmod_a[:, :2 * D], 1e-4, "fused dshift/dscale")
+    if fused_gate:
+        close(dy_b, dy_a, 2 ** -8, "fused dy")
+        close(dmod_b[:, 2 * D:], dmod_a[:, 2 * D:], 1e-4, "fused dgate")
+        close(dbias_b, dbias_a, 1e-4, "fused dbias")
+    else:
+        assert dy_b is None
+    # autograd reference of the LN part, non-accumulating variant
+    xr = x.clone().requires_grad_(True)
+    ln = F.layer_norm(xr, (D,), eps=1e-6).view(B, T, D)
+    ((ln * (1 + scale[:, None, :]) + shift[:, None, :]).view(M, D) * dxmod.float()).sum().backward()
+    g_c = torch.full((M, D), float("nan"), device=dev())
+    dmod_c = torch.zeros(B, 3 * D, device=dev())
+    ops.ln_modulate_bwd_gate(dxmod, x, mean, rstd, scale, 3 * D, T, g_c, False, dmod_c[:, :D], dmod_c[:, D:], 3 * D,
+                             M, D)
+    close(g_c, xr.grad, 1e-3, "fused ln bwd dx (init)")
+
+
 @pytest.mark.parametrize("D,T,B", [(1152, 128, 4), (512, 16, 2)])
 def test_gate_bwd(ops, D, T, B):
     torch.manual_seed(7)

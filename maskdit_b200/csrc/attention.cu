@@ -172,13 +172,13 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
     const float mn0 = fmaxf(m0, quad_max(mx0)), mn1 = fmaxf(m1, quad_max(mx1));
-    const float a0 = exp2f((m0 - mn0) * sl), a1 = exp2f((m1 - mn1) * sl);
+    const float a0 = fast_exp2((m0 - mn0) * sl), a1 = fast_exp2((m1 - mn1) * sl);
     m0 = mn0, m1 = mn1;
     float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < kTile / 8; ++nt) {
-      s[nt][0] = exp2f(s[nt][0] * sl - m0 * sl), s[nt][1] = exp2f(s[nt][1] * sl - m0 * sl);
-      s[nt][2] = exp2f(s[nt][2] * sl - m1 * sl), s[nt][3] = exp2f(s[nt][3] * sl - m1 * sl);
+      s[nt][0] = fast_exp2(s[nt][0] * sl - m0 * sl), s[nt][1] = fast_exp2(s[nt][1] * sl - m0 * sl);
+      s[nt][2] = fast_exp2(s[nt][2] * sl - m1 * sl), s[nt][3] = fast_exp2(s[nt][3] * sl - m1 * sl);
       rs0 += s[nt][0] + s[nt][1], rs1 += s[nt][2] + s[nt][3];
     }
     l0 = l0 * a0 + rs0, l1 = l1 * a1 + rs1;
@@ -264,10 +264,10 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 #pragma unroll
     for (int nt = 0; nt < kTile / 8; ++nt) {
       const int c = k0 + nt * 8 + (lane & 3) * 2;
-      const float p0 = (c < T) ? exp2f(s[nt][0] * sl - ls0) : 0.f;
-      const float p1 = (c + 1 < T) ? exp2f(s[nt][1] * sl - ls0) : 0.f;
-      const float p2 = (c < T) ? exp2f(s[nt][2] * sl - ls1) : 0.f;
-      const float p3 = (c + 1 < T) ? exp2f(s[nt][3] * sl - ls1) : 0.f;
+      const float p0 = (c < T) ? fast_exp2(s[nt][0] * sl - ls0) : 0.f;
+      const float p1 = (c + 1 < T) ? fast_exp2(s[nt][1] * sl - ls0) : 0.f;
+      const float p2 = (c < T) ? fast_exp2(s[nt][2] * sl - ls1) : 0.f;
+      const float p3 = (c + 1 < T) ? fast_exp2(s[nt][3] * sl - ls1) : 0.f;
       s[nt][0] = p0 * (dp[nt][0] - dl0) * scale, s[nt][1] = p1 * (dp[nt][1] - dl0) * scale;
       s[nt][2] = p2 * (dp[nt][2] - dl1) * scale, s[nt][3] = p3 * (dp[nt][3] - dl1) * scale;
     }
@@ -334,10 +334,10 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
     for (int nt = 0; nt < kTile / 8; ++nt) {
       const int cl = nt * 8 + (lane & 3) * 2, c = q0 + cl;
       const float e0 = sLse[cl], e1 = sLse[cl + 1], d0 = sDelta[cl], d1 = sDelta[cl + 1];
-      const float p0 = (c < T) ? exp2f(st[nt][0] * sl - e0) : 0.f;
-      const float p1 = (c + 1 < T) ? exp2f(st[nt][1] * sl - e1) : 0.f;
-      const float p2 = (c < T) ? exp2f(st[nt][2] * sl - e0) : 0.f;
-      const float p3 = (c + 1 < T) ? exp2f(st[nt][3] * sl - e1) : 0.f;
+      const float p0 = (c < T) ? fast_exp2(st[nt][0] * sl - e0) : 0.f;
+      const float p1 = (c + 1 < T) ? fast_exp2(st[nt][1] * sl - e1) : 0.f;
+      const float p2 = (c < T) ? fast_exp2(st[nt][2] * sl - e0) : 0.f;
+      const float p3 = (c + 1 < T) ? fast_exp2(st[nt][3] * sl - e1) : 0.f;
       st[nt][0] = p0, st[nt][1] = p1, st[nt][2] = p2, st[nt][3] = p3;
       ds[nt][0] = p0 * (dpt[nt][0] - d0) * scale, ds[nt][1] = p1 * (dpt[nt][1] - d1) * scale;
       ds[nt][2] = p2 * (dpt[nt][2] - d0) * scale, ds[nt][3] = p3 * (dpt[nt][3] - d1) * scale;

@@ -14,7 +14,11 @@
 // SBO = ROWBLK) and as an MN-major operand (contraction over tokens: SBO = 128, LBO = ROWBLK), so Q, K, V, dO, P and dS
 // are each staged exactly once.  head_dim 72 -> 9 real 16-byte chunks + 1 zero chunk per row (144-byte rows cannot
 // be TMA-swizzled; the tiles are filled with coalesced 16-byte loads instead).
+#include <stdlib.h>
+#include <string.h>
+
 #include "attention_tc.cuh"
+#include "gemm.h"
 #include "../../include/maskdit_b200.h"
 
 namespace mdt {
@@ -31,10 +35,16 @@ constexpr int fwd_v_offset(int dp, int tk) {
 // thread per row was measured faster (114 vs 121 us at B=256, d_h=72: the extra barrier costs more than it saves)
 constexpr int fwd_tpr(int tk) { return tk >= 256 ? 2 : 1; }
 
-template <int DP, int TK>
+// Tile fill.  r01 phase timing (clock64 around the phases of a one-CTA-per-SM variant): ISSUING the 16-byte cp.async
+// of one item (60 KB at T = 128, d_h = 72) took 3.9k of the 8.9k cycles an item needs - the LSU accepts ~16 B/clk
+// per SM of such requests - and a persistent double-buffered variant was slower than this kernel for that reason.
+// With kTMA the tiles are written by TMA instead (4-D tensor map, see make_token_tile_tmap: the box lands directly
+// in the core-matrix layout): one warp issues <= 3 bulk copies per lane and nothing else touches the LSU.  Rows of
+// d_h = 72 are copied as 9 chunks per 8-row block (one box each) so that the zero pad chunk stays zero.
+template <int DP, int TK, bool kTMA>
 __global__ void __launch_bounds__(kQB * fwd_tpr(TK))
-attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
-                   int T, int H, int dh, float scale) {
+attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __grid_constant__ CUtensorMap tm_qkv,
+                   __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, int dh, float scale) {
   using TT = TokTile<DP>;
   constexpr int kPBlk = (TK / 8) * 128;                       // bytes per 8-query block of P
   constexpr int kTmemCols = TK;  // O aliases S: S is dead once every row thread has written its P row to smem
@@ -47,7 +57,8 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
   const uint32_t sP = sQ;
   float* s_red = reinterpret_cast<float*>(smem + kVOff + TK * DP * 2);  // [2][128] row max, [2][128] row sum
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + 4 * kQB);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* ld_bar = bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kQB - 1), half = tid >> 7;
   const int b = blockIdx.y / H, h = blockIdx.y % H, q0 = blockIdx.x * kQB;
@@ -56,12 +67,44 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
   if (warp == 0) tmem_alloc<kTmemCols>(tmem_slot);
   if (tid == 0) {
     mbar_init(bar, 1);
+    mbar_init(ld_bar, 1);
     fence_barrier_init();
   }
-  TT::load(sQ, base + q0 * rs + h * dh, rs, kQB, dh);
-  TT::load(sK, base + (H + h) * dh, rs, TK, dh);
-  TT::load(sV, base + (2 * H + h) * dh, rs, TK, dh);
-  cp_async_wait_all();
+  if constexpr (kTMA) {
+    __syncthreads();  // barrier init visible to the issuing warp
+    if (warp == 1) {
+      const int lane = tid & 31;
+      if (lane == 0) mbar_arrive_expect_tx(ld_bar, static_cast<uint32_t>((kQB + 2 * TK) * dh * 2));
+      __syncwarp();
+      // boxes: whole 128-row tiles when d_h == DP, single 8-row blocks (9 of 10 chunks) otherwise
+      const int rb_per_box = (dh == DP) ? kQB / 8 : 1;
+      const int nq = (kQB / 8) / rb_per_box, nk = (TK / 8) / rb_per_box;
+      const int chunks = dh / 8;
+      const int rb0 = static_cast<int>((static_cast<long long>(b) * T) / 8);
+      for (int i = lane; i < nq + 2 * nk; i += 32) {
+        int sel, j;
+        uint32_t dst;
+        if (i < nq) sel = 0, j = i, dst = sQ;
+        else if (i < nq + nk) sel = 1, j = i - nq, dst = sK;
+        else sel = 2, j = i - nq - nk, dst = sV;
+        const int rblk = j * rb_per_box;
+        tma_load_4d(&tm_qkv, ld_bar, dst + rblk * TT::ROWBLK, 0, 0, (sel * H + h) * chunks,
+                    rb0 + (sel == 0 ? q0 / 8 : 0) + rblk);
+      }
+    }
+    if (dh < DP) {  // the pad chunk of every row is never written by TMA: zero it (generic proxy -> fence below)
+      for (int r = tid; r < kQB + 2 * TK; r += blockDim.x) {
+        const uint32_t tile = r < kQB ? sQ : (r < kQB + TK ? sK : sV);
+        const int rr = r < kQB ? r : (r < kQB + TK ? r - kQB : r - kQB - TK);
+        for (int c8 = dh / 8; c8 < DP / 8; ++c8) sts128u(tile + TT::off(rr, c8), make_uint4(0, 0, 0, 0));
+      }
+    }
+  } else {
+    TT::load(sQ, base + q0 * rs + h * dh, rs, kQB, dh);
+    TT::load(sK, base + (H + h) * dh, rs, TK, dh);
+    TT::load(sV, base + (2 * H + h) * dh, rs, TK, dh);
+    cp_async_wait_all();
+  }
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
@@ -69,6 +112,7 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tO = tmem;
   if (tid == 0) {
+    if constexpr (kTMA) mbar_wait(ld_bar, 0);
     mma_kk<DP>(tS, sQ, sK, TK, false);
     umma_commit(bar);
   }
@@ -107,7 +151,7 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
       float p[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        p[j] = exp2f(__uint_as_float(r[8 * g + j]) * sl - msl);
+        p[j] = fast_exp2(__uint_as_float(r[8 * g + j]) * sl - msl);
         l += p[j];
       }
       sts128u(prow + (c / 8 + g) * 128,
@@ -158,11 +202,15 @@ constexpr int kBwdThreads = 256;  // two threads per query / key row: each owns 
 // second tile set while item i is being computed (a per-item CTA spent 8k of its 18k cycles waiting for its tiles).
 // delta = rowsum(dO * O):  NB == 1 uses the identity  sum_d dO*O = sum_k P*dP  on the S / dP accumulators already in
 // TMEM (no O tile at all); NB == 2 stages O as a fifth tile of the set.
-template <int DP, int NB>
+// kTMA: the tile sets are filled by TMA (one warp issues the boxes, completion on a per-set mbarrier) instead of
+// cp.async by all threads - see the note at attn_tc_fwd_kernel; the zero pad chunks are written once at kernel start.
+template <int DP, int NB, bool kTMA>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
-                   const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
-                   __nv_bfloat16* __restrict__ dqkv, int H, int dh, float scale, int nitems) {
+                   const __nv_bfloat16* __restrict__ dout, const __grid_constant__ CUtensorMap tm_qkv,
+                   const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_o,
+                   const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int H, int dh, float scale,
+                   int nitems) {
   using TT = TokTile<DP>;
   constexpr int T = NB * kQB;
   constexpr bool kDeltaFromP = NB == 1;
@@ -177,7 +225,8 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
   const uint32_t sP = s0 + 2 * kSetBytes, sdS = sP + kQB * kQB * 2;
   float* s_part = reinterpret_cast<float*>(smem + 2 * kSetBytes + 2 * kQB * kQB * 2);  // [2][128] partial deltas
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_part + 2 * kQB);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* ld_bar = bar + 1;  // [2]: one per tile set (kTMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row = tid & (kQB - 1), half = tid >> 7;  // TMEM lane (= row) is fixed by warp % 4, `half` picks the columns
@@ -186,20 +235,50 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
   if (warp == 0) tmem_alloc<512>(tmem_slot);
   if (tid == 0) {
     mbar_init(bar, 1);
+    mbar_init(&ld_bar[0], 1);
+    mbar_init(&ld_bar[1], 1);
     fence_barrier_init();
   }
-  auto issue_loads = [&](int item, uint32_t set) {
+  if constexpr (kTMA) {
+    if (dh < DP) {  // pad chunks of both sets: zero once, TMA never writes them
+      for (int r = tid; r < 2 * kSetTiles * T; r += blockDim.x)
+        for (int c8 = dh / 8; c8 < DP / 8; ++c8)
+          sts128u(s0 + (r / T) * kTileBytes + TT::off(r % T, c8), make_uint4(0, 0, 0, 0));
+      fence_proxy_async_smem();
+    }
+    __syncthreads();  // barrier init (and the zeroed pads) visible before the first bulk copy is issued
+  }
+  constexpr int kLoadWarp = 7;
+  auto issue_loads = [&](int item, int set_idx) {
+    const uint32_t set = s0 + set_idx * kSetBytes;
     const int b = item / H, h = item % H;
-    const __nv_bfloat16* base = qkv + static_cast<long long>(b) * T * rs;
-    TT::load(set, base + h * dh, rs, T, dh);
-    TT::load(set + kTileBytes, base + (H + h) * dh, rs, T, dh);
-    TT::load(set + 2 * kTileBytes, base + (2 * H + h) * dh, rs, T, dh);
-    TT::load(set + 3 * kTileBytes, dout + static_cast<long long>(b) * T * HD + h * dh, HD, T, dh);
-    if constexpr (!kDeltaFromP) TT::load(set + 4 * kTileBytes, out + static_cast<long long>(b) * T * HD + h * dh, HD, T, dh);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    if constexpr (kTMA) {
+      if (warp != kLoadWarp) return;
+      const int lane = tid & 31;
+      if (lane == 0) mbar_arrive_expect_tx(&ld_bar[set_idx], static_cast<uint32_t>(kSetTiles * T * dh * 2));
+      __syncwarp();
+      const int rb_per_box = (dh == DP) ? kQB / 8 : 1;
+      const int per_tile = (T / 8) / rb_per_box, chunks = dh / 8;
+      const int rb0 = static_cast<int>((static_cast<long long>(b) * T) / 8);
+      for (int i = lane; i < kSetTiles * per_tile; i += 32) {
+        const int tile = i / per_tile, rblk = (i - tile * per_tile) * rb_per_box;
+        const uint32_t dst = set + tile * kTileBytes + rblk * TT::ROWBLK;
+        if (tile < 3) tma_load_4d(&tm_qkv, &ld_bar[set_idx], dst, 0, 0, (tile * H + h) * chunks, rb0 + rblk);
+        else tma_load_4d(tile == 3 ? &tm_do : &tm_o, &ld_bar[set_idx], dst, 0, 0, h * chunks, rb0 + rblk);
+      }
+    } else {
+      const __nv_bfloat16* base = qkv + static_cast<long long>(b) * T * rs;
+      TT::load(set, base + h * dh, rs, T, dh);
+      TT::load(set + kTileBytes, base + (H + h) * dh, rs, T, dh);
+      TT::load(set + 2 * kTileBytes, base + (2 * H + h) * dh, rs, T, dh);
+      TT::load(set + 3 * kTileBytes, dout + static_cast<long long>(b) * T * HD + h * dh, HD, T, dh);
+      if constexpr (!kDeltaFromP)
+        TT::load(set + 4 * kTileBytes, out + static_cast<long long>(b) * T * HD + h * dh, HD, T, dh);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
   };
   int item = blockIdx.x;
-  if (item < nitems) issue_loads(item, s0);
+  if (item < nitems) issue_loads(item, 0);
   float lse_next[NB];
 #pragma unroll
   for (int qb = 0; qb < NB; ++qb)
@@ -226,13 +305,14 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     // prefetch the next item into the other set (its last readers, the MMAs of item it-1, completed before that item's
     // read-out) and this row's next lse values
     if (nxt < nitems) {
-      issue_loads(nxt, s0 + ((it + 1) & 1) * kSetBytes);
+      issue_loads(nxt, (it + 1) & 1);
 #pragma unroll
       for (int qb = 0; qb < NB; ++qb) lse_next[qb] = lse[static_cast<long long>(nxt) * T + qb * kQB + row];
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      if constexpr (!kTMA) asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if constexpr (!kTMA) asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
+    if constexpr (kTMA) mbar_wait(&ld_bar[it & 1], (it >> 1) & 1);
     fence_proxy_async_smem();
     tcgen05_fence_before();
     __syncthreads();
@@ -281,7 +361,7 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
             tcgen05_wait_ld();
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              part = fmaf(exp2f(__uint_as_float(rs_[j]) * sl - lsl), __uint_as_float(rp[j]), part);
+              part = fmaf(fast_exp2(__uint_as_float(rs_[j]) * sl - lsl), __uint_as_float(rp[j]), part);
           }
           s_part[half * kQB + row] = part;
           __syncthreads();
@@ -299,7 +379,7 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
             float p[8], ds[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              p[j] = exp2f(__uint_as_float(rs_[8 * g + j]) * sl - lsl);
+              p[j] = fast_exp2(__uint_as_float(rs_[8 * g + j]) * sl - lsl);
               ds[j] = p[j] * (__uint_as_float(rp[8 * g + j]) - delta) * scale;
             }
             const uint32_t o = prow + (c / 8 + g) * 128;
@@ -377,30 +457,63 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 // ------------------------------------------------------------------------------------------------------------
 // host dispatch (called from attention.cu)
 // ------------------------------------------------------------------------------------------------------------
+static bool attn_tma() {  // MDT_ATTN_TMA=0: cp.async tile fill (A/B switch)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MDT_ATTN_TMA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <int DP, int TK>
 static int launch_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale,
                       cudaStream_t st) {
   const int smem = fwd_v_offset(DP, TK) + TK * DP * 2 + 4 * kQB * 4 + 64;
-  auto kern = attn_tc_fwd_kernel<DP, TK>;
   static bool set = false;
   if (!set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return MDT_ERR_CUDA;
+    if (cudaFuncSetAttribute(attn_tc_fwd_kernel<DP, TK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(attn_tc_fwd_kernel<DP, TK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+            cudaSuccess)
+      return MDT_ERR_CUDA;
     set = true;
   }
-  kern<<<dim3(T / kQB, B * H), kQB * fwd_tpr(TK), smem, st>>>(static_cast<const __nv_bfloat16*>(qkv),
-                                                 static_cast<__nv_bfloat16*>(out), lse, T, H, dh, scale);
+  const dim3 grid(T / kQB, B * H);
+  const int threads = kQB * fwd_tpr(TK);
+  alignas(64) CUtensorMap tm;
+  // measured (B200, us, TMA vs cp.async): T=128 d_h=72 95 vs 111; T=256 d_h=32 227 vs 199; T=256 d_h=72 186 vs 174 -
+  // with 16-byte inner boxes TMA itself is the slower copy, it only wins where three CTAs per SM hide it
+  const bool tma = attn_tma() && TK == 128 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0;
+  if (tma) {
+    const int rc = make_token_tile_tmap(&tm, qkv, static_cast<unsigned long long>(B) * T, 3ull * H * dh, dh / 8,
+                                        dh == DP ? kQB / 8 : 1);
+    if (rc != MDT_OK) return rc;
+    attn_tc_fwd_kernel<DP, TK, true><<<grid, threads, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv), tm,
+                                                                  static_cast<__nv_bfloat16*>(out), lse, T, H, dh,
+                                                                  scale);
+  } else {
+    memset(&tm, 0, sizeof(tm));
+    attn_tc_fwd_kernel<DP, TK, false><<<grid, threads, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv), tm,
+                                                                   static_cast<__nv_bfloat16*>(out), lse, T, H, dh,
+                                                                   scale);
+  }
   return cudaGetLastError() == cudaSuccess ? MDT_OK : MDT_ERR_CUDA;
 }
 template <int DP, int NB>
 static int launch_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int H,
                       int dh, float scale, cudaStream_t st) {
   constexpr int kSetTiles = (NB == 1) ? 4 : 5;
+  constexpr int T = NB * kQB;
   const int smem = 2 * kSetTiles * NB * kQB * DP * 2 + 2 * kQB * kQB * 2 + 2 * kQB * 4 + 64;
-  auto kern = attn_tc_bwd_kernel<DP, NB>;
   static bool set = false;
   static int sms = 0;
   if (!set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return MDT_ERR_CUDA;
+    if (cudaFuncSetAttribute(attn_tc_bwd_kernel<DP, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(attn_tc_bwd_kernel<DP, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+            cudaSuccess)
+      return MDT_ERR_CUDA;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -408,9 +521,28 @@ static int launch_bwd(const void* qkv, const void* out, const void* dout, const 
     set = true;
   }
   const int nitems = B * H;
-  kern<<<nitems < sms ? nitems : sms, kBwdThreads, smem, st>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
-      static_cast<const __nv_bfloat16*>(dout), lse, static_cast<__nv_bfloat16*>(dqkv), H, dh, scale, nitems);
+  const int grid = nitems < sms ? nitems : sms;
+  alignas(64) CUtensorMap tq, td, to;
+  const bool tma = attn_tma() && ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out) |
+                                   reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
+  if (tma) {
+    const unsigned long long rows = static_cast<unsigned long long>(B) * T;
+    const unsigned rb = dh == DP ? kQB / 8 : 1;
+    int rc = make_token_tile_tmap(&tq, qkv, rows, 3ull * H * dh, dh / 8, rb);
+    if (rc == MDT_OK) rc = make_token_tile_tmap(&td, dout, rows, 1ull * H * dh, dh / 8, rb);
+    if (rc == MDT_OK) rc = make_token_tile_tmap(&to, out, rows, 1ull * H * dh, dh / 8, rb);
+    if (rc != MDT_OK) return rc;
+    attn_tc_bwd_kernel<DP, NB, true><<<grid, kBwdThreads, smem, st>>>(
+        static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
+        static_cast<const __nv_bfloat16*>(dout), tq, td, to, lse, static_cast<__nv_bfloat16*>(dqkv), H, dh, scale,
+        nitems);
+  } else {
+    memset(&tq, 0, sizeof(tq));
+    attn_tc_bwd_kernel<DP, NB, false><<<grid, kBwdThreads, smem, st>>>(
+        static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
+        static_cast<const __nv_bfloat16*>(dout), tq, tq, tq, lse, static_cast<__nv_bfloat16*>(dqkv), H, dh, scale,
+        nitems);
+  }
   return cudaGetLastError() == cudaSuccess ? MDT_OK : MDT_ERR_CUDA;
 }
 

@@ -119,7 +119,7 @@ attn_tcl_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
         float p[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          p[i] = exp2f(__uint_as_float(r[8 * g + i]) * sl - msl);
+          p[i] = fast_exp2(__uint_as_float(r[8 * g + i]) * sl - msl);
           l += p[i];
         }
         sts128u(prow + (c / 8 + g) * 128,
@@ -204,7 +204,7 @@ MDT_DEVINL void softmax_bwd_half(uint32_t tS, uint32_t tdP, uint32_t lane_addr, 
       float p[8], ds[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        p[i] = exp2f(__uint_as_float(rs_[8 * g + i]) * sl - lsl);
+        p[i] = fast_exp2(__uint_as_float(rs_[8 * g + i]) * sl - lsl);
         ds[i] = p[i] * (__uint_as_float(rp[8 * g + i]) - delta) * scale;
       }
       const uint32_t o = prow + (c / 8 + g) * 128;

@@ -28,4 +28,11 @@ struct GemmParams {
 
 int gemm_launch(const mdt_gemm_args& a, cudaStream_t stream);
 
+// Tensor map that makes TMA write attention token tiles directly in the UMMA no-swizzle core-matrix layout
+// (attention_tc.cuh): a row-major bf16 matrix [rows, row_elems] is described as the 4-D tensor
+// {8 elements (16 B), 8 rows, row_elems/8 chunks, rows/8 row blocks}; a box {8, 8, chunks, row_blocks} lands in smem as
+// [row block][chunk][row % 8][16 B].  `m` is a CUtensorMap (opaque here to keep cuda.h out of this header).
+int make_token_tile_tmap(void* m, const void* ptr, unsigned long long rows, unsigned long long row_elems,
+                         unsigned box_chunks, unsigned box_row_blocks);
+
 }  // namespace mdt

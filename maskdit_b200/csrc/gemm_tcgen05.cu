@@ -500,6 +500,20 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t o
   return r == CUDA_SUCCESS ? MDT_OK : MDT_ERR_TMAP;
 }
 
+int make_token_tile_tmap(void* m, const void* ptr, unsigned long long rows, unsigned long long row_elems,
+                         unsigned box_chunks, unsigned box_row_blocks) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return MDT_ERR_DRIVER;
+  if (rows % 8 || row_elems % 8 || (reinterpret_cast<uintptr_t>(ptr) & 15)) return MDT_ERR_ARG;
+  cuuint64_t dims[4] = {8, 8, row_elems / 8, rows / 8};
+  cuuint64_t strides[3] = {row_elems * 2, 16, 8 * row_elems * 2};
+  cuuint32_t box[4] = {8, 8, box_chunks, box_row_blocks};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(static_cast<CUtensorMap*>(m), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MDT_OK : MDT_ERR_TMAP;
+}
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {

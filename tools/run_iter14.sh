@@ -1,0 +1,10 @@
+#!/bin/bash
+timeout 900 python -m pytest tests/test_kernels_gpu.py -q -x -k attention 2>&1 | tail -n 3
+timeout 900 python -m pytest tests/test_model_gpu.py tests/test_entrypoints_gpu.py -q -x 2>&1 | tail -n 5
+python tools/run_attn_time.py
+for gph in 1 0; do
+MDT_CUDA_GRAPH=$gph timeout 600 python bench.py --workload sampler --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('sampler graph=$gph', round(d['value'],2), d['unit'], 'launches', d.get('gpu_launches'), 'clk', d['clocks']['sm_mhz'])"
+done
+timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('train', round(d['value'],1), 'samples/s', round(d['ms_per_step'],2), 'ms', 'gemm', round(d['roofline']['achieved']), 'clk', d['clocks']['sm_mhz'])"

@@ -209,8 +209,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                    const __nv_bfloat16* __restrict__ dout, const __grid_constant__ CUtensorMap tm_qkv,
                    const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_o,
-                   const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int H, int dh, float scale,
-                   int nitems) {
+                   const __grid_constant__ CUtensorMap tm_dqkv, const float* __restrict__ lse,
+                   __nv_bfloat16* __restrict__ dqkv, int H, int dh, float scale, int nitems) {
   using TT = TokTile<DP>;
   constexpr int T = NB * kQB;
   constexpr bool kDeltaFromP = NB == 1;
@@ -249,6 +249,10 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     __syncthreads();  // barrier init (and the zeroed pads) visible before the first bulk copy is issued
   }
   constexpr int kLoadWarp = 7;
+  // NB == 1 with TMA: dQ | dK | dV are staged as bf16 tiles in the (dead) P / dS region and leave through bulk tensor
+  // stores.  r01 phase timing: the direct read-out (every thread storing 16-byte pieces of its own row: 32 half-written
+  // sectors per warp instruction) took 5.8k of the 15.6k cycles of an item.
+  constexpr bool kBulkOut = kTMA && NB == 1;
   auto issue_loads = [&](int item, int set_idx) {
     const uint32_t set = s0 + set_idx * kSetBytes;
     const int b = item / H, h = item % H;
@@ -294,6 +298,12 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
   constexpr uint32_t kBlkBytes = 16 * RB;  // 128 token rows
   uint32_t phase = 0;
 
+#ifdef MDT_ATTN_PROF  // phase cycle counters (tools/attn_phase_prof.py), written to the delta scratch behind lse
+  long long pt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, t_prev = clock64();
+#define MDT_PROF(i) { const long long t_now = clock64(); pt[i] += t_now - t_prev; t_prev = t_now; }
+#else
+#define MDT_PROF(i)
+#endif
   for (int it = 0; item < nitems; ++it, item += gridDim.x) {
     const uint32_t set = s0 + (it & 1) * kSetBytes;
     const uint32_t sQ = set, sK = set + kTileBytes, sV = set + 2 * kTileBytes, sdO = set + 3 * kTileBytes;
@@ -317,6 +327,7 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
+    MDT_PROF(0)  // prefetch issue + load wait + barrier
 
     float delta_all[NB];
     if constexpr (!kDeltaFromP) {
@@ -342,6 +353,7 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
       mma_kk<DP>(tdP, sdO, sV, kQB, false);
       umma_commit(bar);
     }
+    MDT_PROF(1)  // delta from O (NB = 2) + first S / dP issue
     for (int qb = 0; qb < NB; ++qb) {
       const int q = qb * kQB + row;
       float delta = kDeltaFromP ? 0.f : (qb == 0 ? delta_all[0] : delta_all[NB - 1]);
@@ -350,6 +362,7 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
         mbar_wait(bar, phase);
         phase ^= 1;
         tcgen05_fence_after();
+        MDT_PROF(2)  // S / dP MMA wait
         if constexpr (kDeltaFromP) {
           // delta_q = sum_k P[q,k] dP[q,k]; the two threads of a row each sum their 64 keys and meet through smem
           float part = 0.f;
@@ -364,9 +377,13 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
               part = fmaf(fast_exp2(__uint_as_float(rs_[j]) * sl - lsl), __uint_as_float(rp[j]), part);
           }
           s_part[half * kQB + row] = part;
+          if constexpr (kBulkOut) {
+            if (warp == kLoadWarp) bulk_wait_read_all();  // previous item's gradient tiles have left the P / dS region
+          }
           __syncthreads();
           delta = s_part[row] + s_part[kQB + row];
         }
+        MDT_PROF(3)  // delta pass + exchange
         const uint32_t prow = (row >> 3) * kPBlk + (row & 7) * 16;
 #pragma unroll 1
         for (int c = half * (kQB / 2); c < (half + 1) * (kQB / 2); c += 32) {
@@ -392,6 +409,7 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
         fence_proxy_async_smem();
         tcgen05_fence_before();
         __syncthreads();
+        MDT_PROF(4)  // P / dS pass + barrier
         if (tid == 0) {
           tcgen05_fence_after();
           const uint32_t tdK = tKV + kb * 2 * DP, tdV = tdK + DP;
@@ -420,21 +438,25 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
           }
           umma_commit(bar);
         }
+        MDT_PROF(5)  // dV / dK / dQ (+ next S / dP) issue
       }
       // dQ of this query block is complete once the last commit lands; the same commit also covers the next S/dP
       mbar_wait(bar, phase);
       tcgen05_fence_after();
+      MDT_PROF(6)  // gradient MMA wait
       __nv_bfloat16* grow = dqkv + (static_cast<long long>(b) * T + q) * rs + h * dh;
       {
         // the two threads of a row take the two column halves (DP/2 is a multiple of 8 for DP = 32, 64, 80)
         constexpr int HC = DP / 2;
         uint32_t r[HC];
         tmem_ld_cols<HC>(tdQ + lane_addr + half * HC, r);
-        store_row_bf16<HC>(grow, half * HC, r, dh, 1.f);
+        if constexpr (kBulkOut) stage_row_bf16<DP, HC>(sP, row, half * HC / 8, r, dh);
+        else store_row_bf16<HC>(grow, half * HC, r, dh, 1.f);
       }
       // the next iteration's first wait uses the same (already completed) phase: do not flip here
       tcgen05_fence_before();
       __syncthreads();  // all rows read dQ before the next query block's MMAs (queued behind this commit) reuse it
+      MDT_PROF(7)  // dQ read-out + barrier
     }
     phase ^= 1;  // the last commit of the item has been consumed by the wait above
     // dK / dV: rows = keys; threads 0-127 write dK, threads 128-255 write dV
@@ -445,11 +467,37 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
       const uint32_t tacc = tKV + kb * 2 * DP + half * DP;
       uint32_t r[DP];
       tmem_ld_cols<DP>(tacc + lane_addr, r);
-      store_row_bf16<DP>(grow, 0, r, dh, 1.f);
+      if constexpr (kBulkOut) stage_row_bf16<DP, DP>(sP + (1 + half) * kBlkBytes, row, 0, r, dh);
+      else store_row_bf16<DP>(grow, 0, r, dh, 1.f);
     }
+    if constexpr (kBulkOut) fence_proxy_async_smem();
     tcgen05_fence_before();
     __syncthreads();  // accumulators and tiles of this item are dead; the next item may overwrite them
     tcgen05_fence_after();
+    if constexpr (kBulkOut) {
+      if (warp == kLoadWarp) {
+        const int lane = tid & 31;
+        const int rb_per_box = (dh == DP) ? kQB / 8 : 1;
+        const int per_tile = (kQB / 8) / rb_per_box, chunks = dh / 8;
+        const int rb0 = static_cast<int>((static_cast<long long>(b) * T) / 8);
+        for (int i = lane; i < 3 * per_tile; i += 32) {
+          const int tile = i / per_tile, rblk = (i - tile * per_tile) * rb_per_box;
+          tma_store_4d(&tm_dqkv, sP + tile * kBlkBytes + rblk * TT::ROWBLK, 0, 0, (tile * H + h) * chunks, rb0 + rblk);
+        }
+        bulk_commit_group();
+      }
+    }
+    MDT_PROF(8)  // dK / dV read-out + barrier
+  }
+#ifdef MDT_ATTN_PROF
+  if (blockIdx.x == 0 && (tid == 0 || tid == 200)) {
+    float* dst = const_cast<float*>(lse) + static_cast<long long>(nitems) * T + (tid == 0 ? 0 : 16);
+    for (int i = 0; i < 9; ++i) dst[i] = static_cast<float>(pt[i]);
+  }
+#endif
+#undef MDT_PROF
+  if constexpr (kBulkOut) {
+    if (warp == kLoadWarp) bulk_wait_all();
   }
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
@@ -522,26 +570,27 @@ static int launch_bwd(const void* qkv, const void* out, const void* dout, const 
   }
   const int nitems = B * H;
   const int grid = nitems < sms ? nitems : sms;
-  alignas(64) CUtensorMap tq, td, to;
+  alignas(64) CUtensorMap tq, td, to, tg;
   const bool tma = attn_tma() && ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out) |
-                                   reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
+                                   reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dqkv)) & 15) == 0;
   if (tma) {
     const unsigned long long rows = static_cast<unsigned long long>(B) * T;
     const unsigned rb = dh == DP ? kQB / 8 : 1;
     int rc = make_token_tile_tmap(&tq, qkv, rows, 3ull * H * dh, dh / 8, rb);
     if (rc == MDT_OK) rc = make_token_tile_tmap(&td, dout, rows, 1ull * H * dh, dh / 8, rb);
     if (rc == MDT_OK) rc = make_token_tile_tmap(&to, out, rows, 1ull * H * dh, dh / 8, rb);
+    if (rc == MDT_OK) rc = make_token_tile_tmap(&tg, dqkv, rows, 3ull * H * dh, dh / 8, rb);
     if (rc != MDT_OK) return rc;
     attn_tc_bwd_kernel<DP, NB, true><<<grid, kBwdThreads, smem, st>>>(
         static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
-        static_cast<const __nv_bfloat16*>(dout), tq, td, to, lse, static_cast<__nv_bfloat16*>(dqkv), H, dh, scale,
-        nitems);
+        static_cast<const __nv_bfloat16*>(dout), tq, td, to, tg, lse, static_cast<__nv_bfloat16*>(dqkv), H, dh,
+        scale, nitems);
   } else {
     memset(&tq, 0, sizeof(tq));
     attn_tc_bwd_kernel<DP, NB, false><<<grid, kBwdThreads, smem, st>>>(
         static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
-        static_cast<const __nv_bfloat16*>(dout), tq, tq, tq, lse, static_cast<__nv_bfloat16*>(dqkv), H, dh, scale,
-        nitems);
+        static_cast<const __nv_bfloat16*>(dout), tq, tq, tq, tq, lse, static_cast<__nv_bfloat16*>(dqkv), H, dh,
+        scale, nitems);
   }
   return cudaGetLastError() == cudaSuccess ? MDT_OK : MDT_ERR_CUDA;
 }

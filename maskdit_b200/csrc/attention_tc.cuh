@@ -97,6 +97,19 @@ struct TokTile {
   }
 };
 
+// N fp32 values of one row -> bf16 chunks c8_0.. of a token tile in smem (chunks at or beyond dh/8 are skipped)
+template <int DP, int N>
+MDT_DEVINL void stage_row_bf16(uint32_t tile, int row, int c8_0, const uint32_t* r, int dh) {
+#pragma unroll
+  for (int g = 0; g < N / 8; ++g)
+    if ((c8_0 + g) * 8 < dh)
+      sts128u(tile + TokTile<DP>::off(row, c8_0 + g),
+              make_uint4(pack_bf16(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1])),
+                         pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3])),
+                         pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5])),
+                         pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]))));
+}
+
 // C[128 x N] (+)= A[128 x K] * B[N x K]^T, K-major views of token tiles; K = DP
 template <int DP>
 MDT_DEVINL void mma_kk(uint32_t tmem_d, uint32_t sa, uint32_t sb, int n, bool acc0) {

@@ -361,6 +361,8 @@ namespace mdt {
 int attention_tc_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale, cudaStream_t st);
 int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int T,
                      int H, int dh, float scale, cudaStream_t st);
+// attention_sw.cu: head_dim 64 / 72 with TMA-friendly split tiles (T = 128 / 256)
+int attention_sw_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale, cudaStream_t st);
 // attention_tc_long.cu: T = 512 / 1024 (and the T = 256 backward the persistent kernel does not cover)
 int attention_tc_long_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale,
                           cudaStream_t st);
@@ -414,7 +416,9 @@ int mdt_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int 
   dim3 grid((T + kTile - 1) / kTile, B * H);
   const float scale = 1.f / sqrtf(static_cast<float>(dh));
   if (use_tc()) {
-    int rc = attention_tc_fwd(qkv, out, lse, B, T, H, dh, scale, static_cast<cudaStream_t>(stream));
+    int rc = attention_sw_fwd(qkv, out, lse, B, T, H, dh, scale, static_cast<cudaStream_t>(stream));
+    if (rc != MDT_ERR_UNSUPPORTED) return rc;
+    rc = attention_tc_fwd(qkv, out, lse, B, T, H, dh, scale, static_cast<cudaStream_t>(stream));
     if (rc != MDT_ERR_UNSUPPORTED) return rc;
     if (use_tc_long()) {
       rc = attention_tc_long_fwd(qkv, out, lse, B, T, H, dh, scale, static_cast<cudaStream_t>(stream));

@@ -500,6 +500,12 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t o
   return r == CUDA_SUCCESS ? MDT_OK : MDT_ERR_TMAP;
 }
 
+int make_row_tile_tmap(void* m, const void* ptr, unsigned long long rows, unsigned long long row_elems,
+                       unsigned box_cols, unsigned box_rows) {
+  if (box_cols != 64 || box_rows > 256 || (row_elems % 8) || (reinterpret_cast<uintptr_t>(ptr) & 15)) return MDT_ERR_ARG;
+  return make_tmap(static_cast<CUtensorMap*>(m), ptr, row_elems, rows, row_elems, box_cols, box_rows);
+}
+
 int make_token_tile_tmap(void* m, const void* ptr, unsigned long long rows, unsigned long long row_elems,
                          unsigned box_chunks, unsigned box_row_blocks) {
   PFN_encodeTiled enc = get_encode_fn();

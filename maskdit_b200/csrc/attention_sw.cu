@@ -205,6 +205,193 @@ attn_sw_fwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// backward, T = 128 (one key / query block per (b,h)): persistent, one CTA per SM, same phase structure as
+// attn_tc_bwd_kernel<DP, 1> (attention_tc.cu) with split tiles: 8 bulk loads per item (Q, K, V, dO: block A + block B),
+// gradients staged as split tiles in the dead P / dS region and written by 6 bulk stores.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kSwBwdThreads = 256;
+
+// N fp32 values of one row -> bf16 chunks c8_0.. of a 128-row split tile
+template <int DP, int N>
+MDT_DEVINL void stage_row_split(uint32_t tile, int row, int c8_0, const uint32_t* r, int dh) {
+#pragma unroll
+  for (int g = 0; g < N / 8; ++g) {
+    const int c8 = c8_0 + g;
+    if (c8 * 8 >= dh) continue;
+    const uint32_t dst = c8 < 8 ? tile + row * 128 + ((c8 ^ (row & 7)) << 4) : tile + kQB * 128 + row * 16;
+    sts128u(dst, make_uint4(pack_bf16(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1])),
+                            pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3])),
+                            pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5])),
+                            pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]))));
+  }
+}
+
+template <int DP>
+__global__ void __launch_bounds__(kSwBwdThreads, 1)
+attn_sw_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid_constant__ CUtensorMap tm_qkv_b,
+                   const __grid_constant__ CUtensorMap tm_do_a, const __grid_constant__ CUtensorMap tm_do_b,
+                   const __grid_constant__ CUtensorMap tm_g_a, const __grid_constant__ CUtensorMap tm_g_b,
+                   const float* __restrict__ lse, int H, int dh, float scale, int nitems) {
+  constexpr int T = kQB;
+  constexpr int kPBlk = (kQB / 8) * 128;
+  constexpr int kTileBytes = sw_tile_bytes(DP, T);  // 20 KB (DP = 80) / 16 KB (DP = 64): multiples of 1024
+  constexpr int kSetBytes = 4 * kTileBytes;         // Q | K | V | dO
+  static_assert(256 + 3 * DP <= 512, "TMEM budget");
+  static_assert(3 * kTileBytes <= 2 * kQB * kQB * 2, "gradient tiles are staged in the P / dS region");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t s0 = smem_u32(smem);
+  const uint32_t sP = s0 + 2 * kSetBytes, sdS = sP + kQB * kQB * 2;
+  float* s_part = reinterpret_cast<float*>(smem + 2 * kSetBytes + 2 * kQB * kQB * 2);  // [2][128] partial deltas
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_part + 2 * kQB);
+  uint64_t* ld_bar = bar + 1;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid & (kQB - 1), half = tid >> 7;
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(&ld_bar[0], 1);
+    mbar_init(&ld_bar[1], 1);
+    fence_barrier_init();
+  }
+  if constexpr (DP > 64) {  // plane 1 (columns 72..79) of every input tile: zero once, TMA never writes it
+    for (int r = tid; r < 8 * T; r += blockDim.x)
+      sts128u(s0 + (r / T) * kTileBytes + T * 128 + T * 16 + (r % T) * 16, make_uint4(0, 0, 0, 0));
+    fence_proxy_async_smem();
+  }
+  __syncthreads();
+  constexpr int kIoWarp = 7;
+  auto issue_loads = [&](int item, int set_idx) {
+    if (warp != kIoWarp) return;
+    const uint32_t set = s0 + set_idx * kSetBytes;
+    const int b = item / H, h = item % H;
+    if (lane == 0) mbar_arrive_expect_tx(&ld_bar[set_idx], static_cast<uint32_t>(4 * T * dh * 2));
+    __syncwarp();
+    if (lane < 4 || (DP > 64 && lane < 8)) {
+      const int tile = lane & 3;  // 0..2: q, k, v of qkv; 3: dO
+      const uint32_t dst = set + tile * kTileBytes;
+      const int col = (tile < 3 ? tile * H + h : h) * dh, r0 = b * T;
+      if (lane < 4) tma_load_2d(tile < 3 ? &tm_qkv_a : &tm_do_a, &ld_bar[set_idx], smem + (dst - s0), col, r0);
+      else tma_load_4d(tile < 3 ? &tm_qkv_b : &tm_do_b, &ld_bar[set_idx], dst + T * 128, 0, 0, col / 8 + 8, r0 / 8);
+    }
+  };
+  int item = blockIdx.x;
+  if (item < nitems) issue_loads(item, 0);
+  float lse_next = item < nitems ? lse[static_cast<long long>(item) * T + row] : 0.f;
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256, tdK = tdQ + DP, tdV = tdK + DP;
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const float sl = scale * 1.4426950408889634f;
+  uint32_t phase = 0;
+
+  for (int it = 0; item < nitems; ++it, item += gridDim.x) {
+    const uint32_t set = s0 + (it & 1) * kSetBytes;
+    const SwOp oQ = sw_op(set, T, 0), oK = sw_op(set + kTileBytes, T, 0), oV = sw_op(set + 2 * kTileBytes, T, 0),
+               odO = sw_op(set + 3 * kTileBytes, T, 0);
+    const int b = item / H, h = item % H;
+    const int nxt = item + gridDim.x;
+    const float lsl = lse_next * 1.4426950408889634f;
+    // prefetch the next item into the other set: its last readers (the MMAs of item it-1) completed before that
+    // item's read-out
+    if (nxt < nitems) {
+      issue_loads(nxt, (it + 1) & 1);
+      lse_next = lse[static_cast<long long>(nxt) * T + row];
+    }
+    if (tid == 0) {
+      mbar_wait(&ld_bar[it & 1], (it >> 1) & 1);
+      sw_mma_kk<DP>(tS, oQ, oK, kQB);
+      sw_mma_kk<DP>(tdP, odO, oV, kQB);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tcgen05_fence_after();
+    // one pass over S / dP: P stays in registers, delta_q = sum_k P dP meets the other half of the row through smem
+    constexpr int kCols = kQB / 2;
+    uint32_t pr[kCols], dpr[kCols];
+    float part = 0.f;
+#pragma unroll
+    for (int c = 0; c < kCols; c += 32) {
+      tmem_ld_32x32b_x32(tS + lane_addr + half * kCols + c, pr + c);
+      tmem_ld_32x32b_x32(tdP + lane_addr + half * kCols + c, dpr + c);
+    }
+    tcgen05_wait_ld();
+#pragma unroll
+    for (int j = 0; j < kCols; ++j) {
+      const float p = fast_exp2(__uint_as_float(pr[j]) * sl - lsl);
+      pr[j] = __float_as_uint(p);
+      part = fmaf(p, __uint_as_float(dpr[j]), part);
+    }
+    s_part[half * kQB + row] = part;
+    if (warp == kIoWarp) bulk_wait_read_all();  // previous item's gradient tiles have left the P / dS region
+    __syncthreads();
+    const float delta = s_part[row] + s_part[kQB + row];
+    const uint32_t prow = (row >> 3) * kPBlk + (row & 7) * 16 + half * (kCols / 8) * 128;
+#pragma unroll
+    for (int g = 0; g < kCols / 8; ++g) {
+      float p[8], ds[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        p[j] = __uint_as_float(pr[8 * g + j]);
+        ds[j] = p[j] * (__uint_as_float(dpr[8 * g + j]) - delta) * scale;
+      }
+      sts128u(sP + prow + g * 128, make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]),
+                                              pack_bf16(p[6], p[7])));
+      sts128u(sdS + prow + g * 128, make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]),
+                                               pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7])));
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tcgen05_fence_after();
+      // dV = P^T dO ; dK = dS^T Q (contraction over the queries) ; dQ = dS K (contraction over the keys)
+      sw_mma_tok<DP>(tdV, make_smem_desc_nosw(sP, kPBlk, 128), (2 * kPBlk) >> 4, 1, odO, false);
+      sw_mma_tok<DP>(tdK, make_smem_desc_nosw(sdS, kPBlk, 128), (2 * kPBlk) >> 4, 1, oQ, false);
+      sw_mma_tok<DP>(tdQ, make_smem_desc_nosw(sdS, 128, kPBlk), 256 >> 4, 0, oK, false);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tcgen05_fence_after();
+    {  // stage dQ (column halves) | dK (threads 0-127) | dV (threads 128-255) as split tiles in the P / dS region
+      constexpr int HC = DP / 2;
+      uint32_t r[DP];
+      tmem_ld_cols<HC>(tdQ + lane_addr + half * HC, r);
+      stage_row_split<DP, HC>(sP, row, half * HC / 8, r, dh);
+      tmem_ld_cols<DP>((half ? tdV : tdK) + lane_addr, r);
+      stage_row_split<DP, DP>(sP + (1 + half) * kTileBytes, row, 0, r, dh);
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();  // accumulators and tiles of this item are dead; the next item may overwrite them
+    tcgen05_fence_after();
+    if (warp == kIoWarp) {
+      if (lane < 3 || (DP > 64 && lane < 6)) {
+        const int tile = lane % 3;  // dq, dk, dv
+        const uint32_t src = sP + tile * kTileBytes;
+        const int col = (tile * H + h) * dh, r0 = b * T;
+        if (lane < 3) tma_store_2d(&tm_g_a, src, col, r0);
+        else tma_store_4d(&tm_g_b, src + T * 128, 0, 0, col / 8 + 8, r0 / 8);
+      }
+      bulk_commit_group();
+    }
+  }
+  if (warp == kIoWarp) bulk_wait_all();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------------------
 static bool attn_sw() {  // MDT_ATTN_SW=0: the no-swizzle kernels of attention_tc.cu (A/B switch)
@@ -251,6 +438,52 @@ int attention_sw_fwd(const void* qkv, void* out, float* lse, int B, int T, int H
     if (T == 128) return launch_sw_fwd<64, 128>(qkv, out, lse, B, T, H, dh, scale, st);
     if (T == 256) return launch_sw_fwd<64, 256>(qkv, out, lse, B, T, H, dh, scale, st);
   }
+  return MDT_ERR_UNSUPPORTED;
+}
+
+template <int DP>
+static int launch_sw_bwd(const void* qkv, const void* dout, const float* lse, void* dqkv, int B, int H, int dh,
+                         float scale, cudaStream_t st) {
+  constexpr int T = kQB;
+  const int smem = 8 * sw_tile_bytes(DP, T) + 2 * kQB * kQB * 2 + 2 * kQB * 4 + 64 + 1024;
+  auto kern = attn_sw_bwd_kernel<DP>;
+  static bool set = false;
+  static int sms = 0;
+  if (!set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return MDT_ERR_CUDA;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    set = true;
+  }
+  alignas(64) CUtensorMap tm[6];
+  const unsigned long long rows = static_cast<unsigned long long>(B) * T;
+  const void* ptrs[3] = {qkv, dout, dqkv};
+  const unsigned long long cols[3] = {3ull * H * dh, 1ull * H * dh, 3ull * H * dh};
+  for (int i = 0; i < 3; ++i) {
+    int rc = make_row_tile_tmap(&tm[2 * i], ptrs[i], rows, cols[i], 64, kQB);
+    if (rc != MDT_OK) return rc;
+    if (DP > 64) {
+      rc = make_token_tile_tmap(&tm[2 * i + 1], ptrs[i], rows, cols[i], 1, kQB / 8);
+      if (rc != MDT_OK) return rc;
+    } else {
+      memcpy(&tm[2 * i + 1], &tm[2 * i], sizeof(CUtensorMap));
+    }
+  }
+  const int nitems = B * H;
+  kern<<<nitems < sms ? nitems : sms, kSwBwdThreads, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], lse, H, dh,
+                                                                 scale, nitems);
+  return cudaGetLastError() == cudaSuccess ? MDT_OK : MDT_ERR_CUDA;
+}
+
+int attention_sw_bwd(const void* qkv, const void* dout, const float* lse, void* dqkv, int B, int T, int H, int dh,
+                     float scale, cudaStream_t st) {
+  if (!attn_sw() || T != kQB) return MDT_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dqkv)) & 15)
+    return MDT_ERR_UNSUPPORTED;
+  if (dh == 72) return launch_sw_bwd<80>(qkv, dout, lse, dqkv, B, H, dh, scale, st);
+  if (dh == 64) return launch_sw_bwd<64>(qkv, dout, lse, dqkv, B, H, dh, scale, st);
   return MDT_ERR_UNSUPPORTED;
 }
 

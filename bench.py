@@ -289,9 +289,9 @@ def bench_train(args, net, dev, world, rank, R, PK, sync_all, max_over_ranks):
                      "achieved": achieved, "peak": PK["sustained"], "unit": "TFLOP/s",
                      "frac": achieved / PK["sustained"], "peak_source": f"{PK['src']} sustained bf16",
                      # DRAM read+write bytes per launch from the committed `ncu --set full` capture of four consecutive
-                     # launches of this kernel inside a step (profiles/r01_gemm_ncu_full_v2.json: 646, 741, 268,
-                     # 421 MB against 690, 690, 310, 456 MB algorithmic) - average, bytes
-                     "traffic": 519e6 if R == 32 and B == 256 else None,
+                     # launches of this kernel inside a step (profiles/r01_gemm_ncu_full_v3.json: 647, 751, 268,
+                     # 420 MB against 690, 690, 310, 456 MB algorithmic) - average, bytes
+                     "traffic": 521e6 if R == 32 and B == 256 else None,
                      "launches_per_step": len(prof), "share_of_step": gemm_ms / ms_step,
                      "step_achieved": sps / world * flop / 1e12, "step_frac": sps / world * flop / 1e12 / PK["sustained"]},
     }

@@ -93,6 +93,9 @@ struct UnitSched {
 // or 64 bytes (bf16), and bias / gate / residual / aux are read with the same coalesced vector pattern.
 // The per-epilogue loops are separate template instances selected by ONE switch per chunk, so a launch only ever
 // touches the instructions of its own epilogue (ncu v3 showed the epilogue instruction-fetch bound).
+#ifdef MDT_GEMM_PROF
+__device__ float g_gemm_prof[8];
+#endif
 constexpr int kStgStride = 36;
 constexpr int kStgFloats = 32 * kStgStride;
 
@@ -266,6 +269,13 @@ MDT_DEVINL void epilogue_loop(const GemmParams& p, UnitSched& sched, uint64_t* t
   };
   int as = 0;
   uint32_t aphase = 0;
+#ifdef MDT_GEMM_PROF  // phase cycle counters of one epilogue warp (tools/gemm_phase_prof.py)
+  long long pt[5] = {0, 0, 0, 0, 0}, t_prev = clock64();
+  int n_tiles = 0;
+#define MDT_GPROF(i) { const long long t_now = clock64(); pt[i] += t_now - t_prev; t_prev = t_now; }
+#else
+#define MDT_GPROF(i)
+#endif
   bool have = sched.next();
   while (have) {
     int row_base, nrows, col_base;
@@ -274,6 +284,7 @@ MDT_DEVINL void epilogue_loop(const GemmParams& p, UnitSched& sched, uint64_t* t
     while (!mbar_try_wait(&tmem_full_bar[as], aphase)) {
     }
     tcgen05_fence_after();
+    MDT_GPROF(0)  // waiting for the accumulator
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * BLOCK_N +
                            col_half * kColsPerWarp;
 #pragma unroll 1
@@ -285,17 +296,20 @@ MDT_DEVINL void epilogue_loop(const GemmParams& p, UnitSched& sched, uint64_t* t
       uint32_t rc[32];
       tmem_ld_32x32b_x32(taddr + ci * 32, rc);
       tcgen05_wait_ld();
+      MDT_GPROF(1)  // operand load issue + tcgen05.ld
       if (nrows > 0 && col0 < p.N) {  // warp-uniform
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           sts128(stg + (lane * kStgStride + 4 * q) * 4, __uint_as_float(rc[4 * q]), __uint_as_float(rc[4 * q + 1]),
                  __uint_as_float(rc[4 * q + 2]), __uint_as_float(rc[4 * q + 3]));
         __syncwarp();
+        MDT_GPROF(2)  // staging stores
         if constexpr (kHasOps || EPI == EPI_ATOMIC) {
           if (c.valid) epilogue_chunk<EPI>(p, stg, c, lane, ops);
           else if (c.col < p.N) epilogue_ragged(p, stg, row_base, nrows, c.col, lane);
         }
         __syncwarp();
+        MDT_GPROF(3)  // transposed read, fused math, global stores
       }
     }
     tcgen05_fence_before();
@@ -305,7 +319,18 @@ MDT_DEVINL void epilogue_loop(const GemmParams& p, UnitSched& sched, uint64_t* t
       else mbar_arrive(&tmem_empty_bar[as]);
     }
     if (++as == 2) as = 0, aphase ^= 1;
+    MDT_GPROF(4)  // release of the accumulator stage
+#ifdef MDT_GEMM_PROF
+    ++n_tiles;
+#endif
   }
+#ifdef MDT_GEMM_PROF
+  if (blockIdx.x == 0 && warp == 5 && lane == 0) {
+    for (int i = 0; i < 5; ++i) g_gemm_prof[i] = static_cast<float>(pt[i]);
+    g_gemm_prof[5] = static_cast<float>(n_tiles);
+  }
+#endif
+#undef MDT_GPROF
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int CG>
@@ -645,3 +670,9 @@ int gemm_launch(const mdt_gemm_args& a, cudaStream_t stream) {
 }
 
 }  // namespace mdt
+
+#ifdef MDT_GEMM_PROF
+extern "C" int mdt_debug_gemm_prof(float* out8) {  // development build only: last launch's epilogue phase cycles
+  return cudaMemcpyFromSymbol(out8, mdt::g_gemm_prof, 8 * sizeof(float)) == cudaSuccess ? 0 : -1;
+}
+#endif

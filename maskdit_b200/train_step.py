@@ -13,6 +13,8 @@ step; the loss is returned as a device tensor (no per-step `.it
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -59,6 +61,14 @@ def lr_at(step: int, base_lr: float, global_batch: int, rampup_kimg: float):
     return base_lr * min(step * global_batch / max(rampup_kimg * 1000, 1e-8), 1)
 
 
+def ar_chunk_bounds(n, k):
+    """[lo, hi) element ranges of the k all-reduce chunks of a flat buffer of n elements (4 KiB aligned starts)."""
+    if k <= 1 or n < k * 1024:
+        return [(0, n)]
+    step = -(-(-(-n // k)) // 1024) * 1024
+    return [(lo, min(n, lo + step)) for lo in range(0, n, step)]
+
+
 class TrainStep:
     def __init__(self, net: EDMPrecond, ema: EDMPrecond | None = None, lr=1e-4, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=0.0, ema_decay=0.9999, loss_fn: EDMLoss | None = None, process_group=None,
@@ -86,6 +96,10 @@ class TrainStep:
         # Overlap: gradient ranges are reduced + stepped on a side stream as soon as a block's backward is enqueued.
         self.overlap = overlap
         self.bg_blocks = 24
+        # gradient all-reduce in this many chunks, pipelined against the optimizer pass (world > 1).  Default 1 = one
+        # flat call: measured on 2 x B200 (same box) 132.0 ms/step flat vs 133.3 ms with 8 chunks - the all-reduce and
+        # the AdamW/EMA pass are both HBM-bound, so running them side by side buys nothing.
+        self.ar_chunks = int(os.environ.get("MDT_AR_CHUNKS", "1"))
         self.side = torch.cuda.Stream(device=dev) if overlap else None
         self._done = []          # [lo, hi) ranges already handled in the current step
         self._lr_now = lr
@@ -96,9 +110,15 @@ class TrainStep:
         st, n = self.st, hi - lo
         if n <= 0:
             return
-        g = st.grad[lo:hi]
         if self.world > 1:
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
+            dist.all_reduce(st.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+        self._step_range(lo, hi, max_blocks)
+
+    def _step_range(self, lo, hi, max_blocks=0):
+        st, n = self.st, hi - lo
+        if n <= 0:
+            return
+        g = st.grad[lo:hi]
         ops.adamw_ema(st.w32[lo:hi], g, self.m[lo:hi], self.v[lo:hi],
                       self.ema_st.w32[lo:hi] if self.ema_st is not None else None, st.w16[lo:hi], n, self._lr_now,
                       self.step_count, self.betas[0], self.betas[1], self.eps, self.wd, self.ema_decay,
@@ -132,6 +152,16 @@ class TrainStep:
                     self._reduce_and_step(cur, lo)
                     cur = max(cur, hi)
             main.wait_stream(self.side)
+        elif self.world > 1 and self.ar_chunks > 1:
+            # The all-reduce is exposed after the backward (overlapping it with the persistent GEMMs costs more than
+            # it hides), but it need not also serialise with the optimizer: the flat gradient is reduced in chunks on
+            # NCCL's stream and the fused AdamW/EMA pass of chunk k runs while chunk k+1 is still on the wire.
+            bounds = ar_chunk_bounds(st.n_train, self.ar_chunks)
+            works = [dist.all_reduce(st.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+                     for lo, hi in bounds]
+            for (lo, hi), w in zip(bounds, works):
+                w.wait()   # the current stream waits for this chunk only
+                self._step_range(lo, hi)
         else:
             self._reduce_and_step(0, st.n_train)   # one flat all-reduce + one optimizer pass
         st.mark_shadow_fresh(self.net._params())   # the kernel refreshed the bf16 shadow itself

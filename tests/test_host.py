@@ -114,6 +114,11 @@ def test_dp_helpers_and_schedule():
         shard_batch(10, 4, 0)
     assert lr_at(0, 1e-4, 1024, 10) == 0.0 and lr_at(5, 1e-4, 1024, 10) == pytest.approx(5.12e-5)
     assert lr_at(100, 1e-4, 1024, 10) == 1e-4
+    from maskdit_b200.train_step import ar_chunk_bounds
+    for n, k in [(730115216, 8), (5000, 8), (1 << 20, 3), (7, 1)]:
+        b = ar_chunk_bounds(n, k)
+        assert b[0][0] == 0 and b[-1][1] == n and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+        assert all(lo % 1024 == 0 for lo, _ in b) and len(b) <= max(k, 1)
 
 
 def _gloo_worker(rank, world, port, q):
@@ -127,7 +132,17 @@ def _gloo_worker(rank, world, port, q):
     lo, hi = shard_batch(8, world, rank)
     flat = full[lo:hi].sum(0)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    q.put((rank, torch.allclose(flat / world, full.sum(0) / world, atol=1e-5)))
+    ok = torch.allclose(flat / world, full.sum(0) / world, atol=1e-5)
+    # chunked, asynchronous form used by TrainStep when world > 1 (optimizer pass of chunk k overlaps chunk k+1)
+    from maskdit_b200.train_step import ar_chunk_bounds
+    big = torch.randn(3, 10000)[rank % 3].clone()
+    ref = big.clone()
+    dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+    works = [(lo, hi, dist.all_reduce(big[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+             for lo, hi in ar_chunk_bounds(big.numel(), 4)]
+    for lo, hi, w in works:
+        w.wait()
+    q.put((rank, ok and len(works) == 4 and torch.equal(big, ref)))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -1,4 +1,5 @@
-// Attention forward for head_dim 64 / 72 with TMA-friendly operand tiles.
+// Attention forward (T = 128 / 256) and backward (T = 128) for head_dim 64 / 72 with TMA-friendly operand tiles
+// (reference: timm Attention core, ctor site models/maskdit.py:178; same math as attention_tc.cu).
 //
 // The no-swizzle core-matrix tiles of attention_tc.cu can only be filled 16 bytes at a time (cp.async, or TMA boxes
 // whose inner extent is 16 bytes): r01 phase timing showed both paths limited to ~16 B/clk per SM, i.e. the tile fill

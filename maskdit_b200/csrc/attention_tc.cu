@@ -1,5 +1,5 @@
 // Attention core on the 5th-gen tensor cores (tcgen05.mma, S / dP / O / dQ / dK / dV accumulators in TMEM) for the
-// MaskDiT training shapes: T = 128 or 256 tokens per sample, head_dim 72 (encoder, zero-padded to 80) or 32 (decoder).
+// MaskDiT training shapes (head_dim 32 runs here; head_dim 64 / 72 prefers the split-tile kernels of attention_sw.cu): T = 128 or 256 tokens per sample, head_dim 72 (encoder, zero-padded to 80) or 32 (decoder).
 // Replaces softmax(q k^T / sqrt(dh)) v of timm Attention (reference ctor site models/maskdit.py:178) and its backward.
 //
 //   forward : CTA = (128 queries of one (b,h)); S = Q K^T -> TMEM; one thread per query row does the softmax straight

@@ -105,6 +105,37 @@ class TrainStep:
         self._lr_now = lr
         net._grad_ready_hook = self._on_grads_ready if overlap else None
 
+    # -- optimizer state for checkpoints (reference: train.py:259-270 stores optimizer.state_dict() under 'opt') ------
+    def state_dict(self):
+        """Per-parameter AdamW state in named_parameters order, laid out like torch.optim.AdamW.state_dict()['state']
+        (exp_avg / exp_avg_sq / step), plus the hyper-parameters; tensors are copies on the current device."""
+        state, names = {}, []
+        for i, (k, p) in enumerate((k, p) for k, p in self.net.named_parameters() if p.requires_grad):
+            lo, _, shape = self.st.offsets[k]
+            n = p.numel()
+            state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.m[lo:lo + n].view(shape).clone(),
+                        "exp_avg_sq": self.v[lo:lo + n].view(shape).clone()}
+            names.append(k)
+        return {"state": state, "param_names": names,
+                "param_groups": [{"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.wd,
+                                  "params": list(range(len(names)))}]}
+
+    def load_state_dict(self, sd):
+        names = sd.get("param_names") or [k for k, p in self.net.named_parameters() if p.requires_grad]
+        if len(names) != len(sd["state"]):
+            raise ValueError(f"optimizer state holds {len(sd['state'])} tensors, the model has {len(names)}")
+        for i, k in enumerate(names):
+            e = sd["state"][i] if i in sd["state"] else sd["state"][str(i)]
+            lo, _, shape = self.st.offsets[k]
+            n = e["exp_avg"].numel()
+            if tuple(e["exp_avg"].shape) != tuple(shape):
+                raise ValueError(f"optimizer state of {k}: shape {tuple(e['exp_avg'].shape)} != {tuple(shape)}")
+            self.m[lo:lo + n].copy_(e["exp_avg"].reshape(-1))
+            self.v[lo:lo + n].copy_(e["exp_avg_sq"].reshape(-1))
+            self.step_count = int(float(e["step"]))
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps, self.wd = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
+
     # -- one gradient range: (all-reduce) + fused AdamW/EMA/bf16-shadow, on the current stream -----------------------
     def _reduce_and_step(self, lo, hi, max_blocks=0):
         st, n = self.st, hi - lo

@@ -238,6 +238,45 @@ def test_train_step_matches_oracle_adamw_and_ema(overlap):
     assert torch.nn.functional.cosine_similarity(e_gpu.flatten(), e_ref.flatten(), dim=0).item() > 0.9
 
 
+def test_train_step_state_dict_resume():
+    """Optimizer state (torch-AdamW-style per-parameter dict) survives a checkpoint round trip: a resumed TrainStep
+    takes bit-identical steps."""
+    import io
+    from maskdit_b200.train_step import TrainStep
+    g = load("s2_train_mask")
+    net, cfg, _ = build()
+    net.train()
+    ema = copy.deepcopy(net).eval()
+    ts = TrainStep(net, ema, lr=1e-3, loss_fn=GoldenLoss(g))
+    x, y = g["images"].cuda(), g["labels"].cuda()
+
+    def one(t):
+        t.loss_fn = GoldenLoss(g)
+        return t.step(x, y, 0.5, 0.1)
+
+    one(ts), one(ts)
+    buf = io.BytesIO()
+    torch.save({"model": net.state_dict(), "ema": ema.state_dict(), "opt": ts.state_dict()}, buf)
+    buf.seek(0)
+    ck = torch.load(buf, map_location="cuda")
+    assert set(ck["opt"]["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and len(ck["opt"]["state"]) == len(
+        [p for p in net.parameters() if p.requires_grad])
+    net2, _, _ = build(seed=5)
+    net2.train()
+    net2.load_state_dict(ck["model"])
+    ema2 = copy.deepcopy(net2).eval()
+    ema2.load_state_dict(ck["ema"])
+    ts2 = TrainStep(net2, ema2, lr=0.5, loss_fn=GoldenLoss(g))
+    ts2.load_state_dict(ck["opt"])
+    assert ts2.step_count == 2 and ts2.lr == 1e-3
+    l1, l2 = one(ts), one(ts2)
+    assert torch.allclose(l1, l2, rtol=1e-6, atol=1e-7)
+    for (k, a), (_, b) in zip(net.state_dict().items(), net2.state_dict().items()):
+        assert torch.allclose(a, b, rtol=0, atol=1e-6), k   # wgrad reductions are atomics: order noise only
+    for (k, a), (_, b) in zip(ema.state_dict().items(), ema2.state_dict().items()):
+        assert torch.allclose(a, b, rtol=0, atol=1e-6), k
+
+
 def test_full_size_config2_properties():
     """BASELINE config 2 at FULL size (XL/2, batch 256, 32x32x4, mask 0.5) through size-independent properties:
     samples are independent through the whole path, so (i) the first rows of a batch-256 loss equal a batch-4 run on

@@ -93,6 +93,8 @@ def main():
         step0 = int(os.path.basename(ck)[:-3]) if os.path.basename(ck)[:-3].isdigit() else 0
     ts = TrainStep(net, ema, lr=cfg.train.lr, lr_rampup_kimg=cfg.train.lr_rampup_kimg, global_batch=global_batch,
                    loss_fn=Losses[cfg.model.precond]())
+    if ck and "opt" in sd and "state" in sd["opt"]:
+        ts.load_state_dict(sd["opt"])
     ratio_fn = mask_ratio_schedule(cfg.model.get("mask_ratio_fn", "constant"), cfg.model.mask_ratio,
                                    cfg.model.get("mask_ratio_min", 0) or 0)
     drop = cfg.model.get("class_dropout_prob", 0) or 0
@@ -124,7 +126,7 @@ def main():
         if step % cfg.log.ckpt_every == 0 and rank == 0:
             d = os.path.join(args.results_dir, "checkpoints")
             os.makedirs(d, exist_ok=True)
-            torch.save({"model": net.state_dict(), "ema": ema.state_dict(), "args": vars(args)},
+            torch.save({"model": net.state_dict(), "ema": ema.state_dict(), "opt": ts.state_dict(), "args": vars(args)},
                        os.path.join(d, f"{step:07d}.pt"))
         if step - step0 >= max_steps:
             break

@@ -326,9 +326,12 @@ def edm_loss(sd, cfg: Cfg, images, labels, rnd_normal, noise_unit, mask_dict, ma
 
 
 def edm_sampler(denoise, latents, num_steps=18, sigma_min=0.002, sigma_max=80.0, rho=7.0, net_sigma_min=0.0,
-                net_sigma_max=float("inf")):
-    """edm_sampler (sample.py:30-66) with S_churn = 0 (gamma = 0, x_hat = x_cur).  `denoise(x_f32, sigma_f64)`
-    returns the network output; state is float64.  Returns (x_final, list of sigmas evaluated)."""
+                net_sigma_max=float("inf"), S_churn=0.0, S_min=0.0, S_max=float("inf"), S_noise=1.0,
+                randn_like=torch.randn_like):
+    """edm_sampler (sample.py:30-66), including the stochastic churn (sample.py:50-53: gamma, t_hat, noise
+    injection; `randn_like` is consumed once per step even when gamma = 0, as in the reference).
+    `denoise(x_f32, sigma_f64)` returns the network output; state is float64.
+    Returns (x_final, list of sigmas evaluated)."""
     sigma_min, sigma_max = max(sigma_min, net_sigma_min), min(sigma_max, net_sigma_max)
     idx = torch.arange(num_steps, dtype=torch.float64)
     t_steps = (sigma_max ** (1 / rho) + idx / (num_steps - 1) * (sigma_min ** (1 / rho) - sigma_max ** (1 / rho))) ** rho
@@ -336,7 +339,10 @@ def edm_sampler(denoise, latents, num_steps=18, sigma_min=0.002, sigma_max=80.0,
     x_next = latents.to(torch.float64) * t_steps[0]
     evals = []
     for i, (t_cur, t_next) in enumerate(zip(t_steps[:-1], t_steps[1:])):
-        x_hat, t_hat = x_next, t_cur
+        x_cur = x_next
+        gamma = min(S_churn / num_steps, math.sqrt(2.0) - 1) if S_min <= t_cur <= S_max else 0
+        t_hat = t_cur + gamma * t_cur
+        x_hat = x_cur + (t_hat ** 2 - t_cur ** 2).sqrt() * S_noise * randn_like(x_cur)
         evals.append(float(t_hat))
         den = denoise(x_hat.float(), t_hat).to(torch.float64)
         d_cur = (x_hat - den) / t_hat

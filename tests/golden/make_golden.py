@@ -142,6 +142,37 @@ def eval_case(name, cfg, B):
     print(name, "sampler |z|", z.abs().mean().item())
 
 
+def churn_case(name, cfg, B):
+    """Sampler with stochastic churn (sample.py:50-53), no guidance: pins gamma / t_hat / noise injection."""
+    net = build_ref(cfg).eval()
+    _, labels = inputs(cfg, B, seed=13)
+    kw = dict(num_steps=8, S_churn=30.0, S_min=0.05, S_max=50.0, S_noise=1.003)
+    with torch.no_grad():
+        rnd = rs.StackedRandomGenerator("cpu", list(range(B)))
+        latents = rnd.randn([B, cfg.img_channels, cfg.img_resolution, cfg.img_resolution])
+        noises, sig_seen = [], []
+
+        def randn_like(x):
+            n = rnd.randn_like(x)
+            noises.append(n.numpy().copy())
+            return n
+
+        orig_forward = net.forward
+
+        def spy(x, sigma, *a, **k):
+            sig_seen.append(float(sigma))
+            return orig_forward(x, sigma, *a, **k)
+
+        net.forward = spy
+        z = rs.edm_sampler(net, latents, labels, randn_like=randn_like, **kw)
+        net.forward = orig_forward
+    assert len(sig_seen) == 15 and len(noises) == 8
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), labels=labels.numpy(), latents=latents.numpy(),
+                        noises=np.stack(noises), z=z.numpy(), sampler_sigmas=np.array(sig_seen),
+                        **{k: np.float64(v) for k, v in kw.items()})
+    print(name, "sampler |z|", z.abs().mean().item(), "sigmas", sig_seen[:4])
+
+
 def table_case():
     out = {}
     for D, g in ((1152, 16), (512, 16), (384, 4), (512, 4), (1152, 32)):
@@ -168,5 +199,9 @@ if __name__ == "__main__":
     train_case("s2_train_nomask", small, B=2, mask_ratio=0.0, with_grads=True)
     eval_case("s2_eval", small, B=2)
     table_case()
+    churn_case("s2_sampler_churn", small, B=2)
+    # another geometry: patch 4 (16 latents per side -> 16 patches), 12 heads of 64, three of four patches masked
+    b4 = O.Cfg(model_type="DiT-B/4", img_resolution=16, num_classes=7)
+    train_case("b4_train_mask75", b4, B=3, mask_ratio=0.75, with_grads=True)
     xl = O.Cfg(model_type="DiT-XL/2", img_resolution=32, num_classes=1000)
     train_case("xl2_c1_fwd", xl, B=2, mask_ratio=0.5, with_grads=False)

@@ -34,9 +34,13 @@ def test_tables_match_reference():
             assert np.array_equal(v.numpy(), g[f"mask_{k}_{L}_{r}"]), (L, r, k)
 
 
-@pytest.mark.parametrize("name", ["s2_train_mask", "s2_train_nomask"])
-def test_train_loss_and_grads_match_reference(name):
+B4 = O.Cfg(model_type="DiT-B/4", img_resolution=16, num_classes=7)  # patch 4, 12 heads of 64, 16 patches
+
+
+@pytest.mark.parametrize("name,CFG", [("s2_train_mask", SMALL), ("s2_train_nomask", SMALL), ("b4_train_mask75", B4)])
+def test_train_loss_and_grads_match_reference(name, CFG):
     g = load(name)
+    SMALL = CFG  # noqa: N806 - the body below is written against the small config's name
     sd = {k: v.requires_grad_(not k.endswith("pos_embed")) for k, v in O.make_state_dict(SMALL, 1).items()}
     mr = float(g["mask_ratio"])
     md = O.mask_from_noise(t(g["mask_noise"]), mr) if mr > 0 else None
@@ -80,6 +84,23 @@ def test_eval_cfg_and_sampler_match_reference():
                                  t(g["latents"]))
     assert len(evals) == 35  # 2N-1 network evaluations
     np.testing.assert_allclose(np.array(evals), g["sampler_sigmas"], rtol=1e-12)
+    np.testing.assert_allclose(z.numpy(), g["z"], rtol=1e-3, atol=1e-4)
+
+
+def test_sampler_with_churn_matches_reference():
+    """Stochastic sampler (S_churn > 0, sample.py:50-53): sigma sequence incl. the inflated t_hat, noise injection."""
+    g = load("s2_sampler_churn")
+    sd = O.make_state_dict(SMALL, 1)
+    noises = [t(n) for n in g["noises"]]
+    lab = t(g["labels"])
+    with torch.no_grad():
+        z, evals = O.edm_sampler(lambda x, s: O.edm_precond(sd, SMALL, x, s, lab, training=False), t(g["latents"]),
+                                 num_steps=int(g["num_steps"]), S_churn=float(g["S_churn"]), S_min=float(g["S_min"]),
+                                 S_max=float(g["S_max"]), S_noise=float(g["S_noise"]),
+                                 randn_like=lambda x: noises.pop(0))
+    assert len(evals) == 15 and not noises
+    np.testing.assert_allclose(np.array(evals), g["sampler_sigmas"], rtol=1e-12)
+    assert evals[1] < evals[2]  # the churned t_hat of step 1 exceeds its t_cur (the previous evaluation's t_next)
     np.testing.assert_allclose(z.numpy(), g["z"], rtol=1e-3, atol=1e-4)
 
 

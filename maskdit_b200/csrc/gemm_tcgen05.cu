@@ -94,7 +94,7 @@ struct UnitSched {
 // The per-epilogue loops are separate template instances selected by ONE switch per chunk, so a launch only ever
 // touches the instructions of its own epilogue (ncu v3 showed the epilogue instruction-fetch bound).
 #ifdef MDT_GEMM_PROF
-__device__ float g_gemm_prof[8];
+__device__ float g_gemm_prof[12];
 #endif
 constexpr int kStgStride = 36;
 constexpr int kStgFloats = 32 * kStgStride;
@@ -433,15 +433,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
+#ifdef MDT_GEMM_PROF  // MMA issuer of CTA 0: cycles waiting for the epilogue / for a full stage / issuing
+    long long mt[3] = {0, 0, 0}, mt_prev = clock64();
+#define MDT_MPROF(i) { const long long t_now = clock64(); mt[i] += t_now - mt_prev; mt_prev = t_now; }
+#else
+#define MDT_MPROF(i)
+#endif
     while (sched.next()) {
       mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
       tcgen05_fence_after();
+      MDT_MPROF(0)  // accumulator stage released by the epilogue
       const uint32_t tmem_d = tmem_base + as * BLOCK_N;
       const bool narrow = BLOCK_N == 256 && (p.N - sched.n_tile() * BLOCK_N) <= BLOCK_N / 2;
       const uint32_t idesc = narrow ? idesc_half : idesc_full;  // half-width MMAs on a ragged last column tile
       for (int kb = sched.kb0; kb < sched.kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
+        MDT_MPROF(1)  // operands of this k-block landed
         const uint32_t sa = smem_u32(smem_tiles + stage * Cfg::kStageBytes);
         const uint32_t sb = sa + Cfg::kABytes;
 #pragma unroll
@@ -459,11 +467,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // frees the smem slot (in both CTAs) once these MMAs retire
         if constexpr (CG == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
         if (++stage == kStages) stage = 0, phase ^= 1;
+        MDT_MPROF(2)  // issue of the k-block's MMAs + commit
       }
       // accumulator complete -> epilogue warps (of both CTAs)
       if constexpr (CG == 2) umma_commit_2sm(&tmem_full_bar[as]); else umma_commit(&tmem_full_bar[as]);
       if (++as == 2) as = 0, aphase ^= 1;
     }
+#ifdef MDT_GEMM_PROF
+    if (blockIdx.x == 0) {
+      g_gemm_prof[6] = static_cast<float>(mt[0]);  // [6] wait accumulator release, [7] wait full stage
+      g_gemm_prof[7] = static_cast<float>(mt[1]);
+      g_gemm_prof[8] = static_cast<float>(mt[2]);  // [8] issue
+    }
+#endif
+#undef MDT_MPROF
   } else if (warp >= 4) {
     // ===================== epilogue (every CTA: its own 128 accumulator rows) =====================
     const uint32_t stg = smem_u32(staging) + (warp - 4) * kStgFloats * 4;
@@ -672,7 +689,7 @@ int gemm_launch(const mdt_gemm_args& a, cudaStream_t stream) {
 }  // namespace mdt
 
 #ifdef MDT_GEMM_PROF
-extern "C" int mdt_debug_gemm_prof(float* out8) {  // development build only: last launch's epilogue phase cycles
-  return cudaMemcpyFromSymbol(out8, mdt::g_gemm_prof, 8 * sizeof(float)) == cudaSuccess ? 0 : -1;
+extern "C" int mdt_debug_gemm_prof(float* out12) {  // development build only: last launch's phase cycles
+  return cudaMemcpyFromSymbol(out12, mdt::g_gemm_prof, 12 * sizeof(float)) == cudaSuccess ? 0 : -1;
 }
 #endif

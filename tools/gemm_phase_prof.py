@@ -19,11 +19,12 @@ def run(tag, M, N, K, epi, **kw):
     for _ in range(5): L.gemm(A, B, M, N, K, out=out, epi=epi, **kw)
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 5 * 1e3
-    buf = (ctypes.c_float * 8)()
+    buf = (ctypes.c_float * 12)()
     assert lib.mdt_debug_gemm_prof(buf) == 0
     v = list(buf); nt = max(v[5], 1)
     print(f"{tag}: {us:.0f} us, {2*M*N*K/us/1e6:.0f} TF/s, {nt:.0f} tiles/CTA; cycles per tile: " +
-          ", ".join(f"{n} {v[i]/nt:.0f}" for i, n in enumerate(names)) + f"; total {sum(v[:5])/nt:.0f}")
+          ", ".join(f"{n} {v[i]/nt:.0f}" for i, n in enumerate(names)) + f"; total {sum(v[:5])/nt:.0f}" +
+          f" | MMA issuer per tile: wait accumulator release {v[6]/nt:.0f}, wait full stage {v[7]/nt:.0f}, issue {v[8]/nt:.0f}")
 M = 32768
 bias = lambda n: torch.randn(n, device=dev)
 run("qkv store   ", M, 3456, 1152, EPI_STORE, bias=bias(3456))

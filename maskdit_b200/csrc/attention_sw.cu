@@ -28,18 +28,33 @@ struct SwOp {
   uint32_t b;      // block B plane 0 address of the slice's first row
   uint32_t plane;  // bytes between the two planes of block B (= 16 * rows of the whole tile)
 };
-MDT_DEVINL SwOp sw_op(uint32_t tile, int tile_rows, int row0) {
-  return SwOp{tile + row0 * 128u, tile + tile_rows * 128u + row0 * 16u, tile_rows * 16u};
+// Block A holds min(DP, 64) columns: 128-byte rows in SWIZZLE_128B atoms for head_dim 64 / 72, 64-byte rows in
+// SWIZZLE_64B atoms for head_dim 32 (decoder; forward only so far and NOT yet validated on hardware: dispatched only
+// with MDT_ATTN_SW64=1).
+constexpr int sw_row_bytes(int dp) { return dp >= 64 ? 128 : dp * 2; }
+MDT_DEVINL SwOp sw_op(uint32_t tile, int tile_rows, int row0, uint32_t row_bytes = 128u) {
+  return SwOp{tile + row0 * row_bytes, tile + tile_rows * row_bytes + row0 * 16u, tile_rows * 16u};
 }
 constexpr int sw_tile_bytes(int dp, int rows) { return rows * dp * 2; }
+// descriptor of a block-A operand: SWIZZLE_128B (layout type 2) or SWIZZLE_64B (layout type 4); SBO = 8 rows
+template <int DP>
+MDT_DEVINL uint64_t sw_desc(uint32_t addr, uint32_t lbo) {
+  if constexpr (DP >= 64) {
+    return make_smem_desc_sw128(addr, lbo, 1024);
+  } else {
+    uint64_t d = make_smem_desc_nosw(addr, lbo, 8 * sw_row_bytes(DP));  // version bit set, layout bits clear
+    return d | (4ull << 61);
+  }
+}
 
 // D[128 x n] = A[128 x DP] * B[n x DP]^T   (both K-major: contraction over head_dim)
 template <int DP>
 MDT_DEVINL void sw_mma_kk(uint32_t tmem_d, SwOp a, SwOp b, int n) {
   const uint32_t idesc = make_idesc_bf16(kQB, n, 0, 0);
-  const uint64_t da = make_smem_desc_sw128(a.a, 16, 1024), db = make_smem_desc_sw128(b.a, 16, 1024);
+  const uint64_t da = sw_desc<DP>(a.a, 16), db = sw_desc<DP>(b.a, 16);
+  constexpr int kSteps = (DP >= 64 ? 64 : DP) / 16;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : 0u);  // +32 B per k-step
+  for (int k = 0; k < kSteps; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : 0u);  // +32 B per k-step
   if constexpr (DP > 64)
     umma_bf16(tmem_d, make_smem_desc_nosw(a.b, a.plane, 128), make_smem_desc_nosw(b.b, b.plane, 128), idesc, 1u);
 }
@@ -48,14 +63,15 @@ MDT_DEVINL void sw_mma_kk(uint32_t tmem_d, SwOp a, SwOp b, int n) {
 // a_desc0 / a_step: descriptor of A's first k-step and its increment (in 16-byte units) per 16 tokens
 template <int DP>
 MDT_DEVINL void sw_mma_tok(uint32_t tmem_d, uint64_t a_desc0, uint32_t a_step, int a_mn, SwOp b, bool acc0) {
-  const uint32_t i64 = make_idesc_bf16(kQB, 64, a_mn, 1), i16 = make_idesc_bf16(kQB, 16, a_mn, 1);
-  const uint64_t db = make_smem_desc_sw128(b.a, 8192, 1024);
+  constexpr int kNA = DP >= 64 ? 64 : DP;  // output columns that come from block A
+  const uint32_t i64 = make_idesc_bf16(kQB, kNA, a_mn, 1), i16 = make_idesc_bf16(kQB, 16, a_mn, 1);
+  const uint64_t db = sw_desc<DP>(b.a, 8192);
   const uint64_t db2 = make_smem_desc_nosw(b.b, 128, b.plane);
 #pragma unroll
   for (int k = 0; k < kQB / 16; ++k) {
     const uint64_t da = a_desc0 + static_cast<uint64_t>(k) * a_step;
     const uint32_t acc = (acc0 || k > 0) ? 1u : 0u;
-    umma_bf16(tmem_d, da, db + static_cast<uint64_t>(k) * (2048 >> 4), i64, acc);
+    umma_bf16(tmem_d, da, db + static_cast<uint64_t>(k) * ((16 * sw_row_bytes(DP)) >> 4), i64, acc);
     if constexpr (DP > 64) umma_bf16(tmem_d + 64, da, db2 + static_cast<uint64_t>(k) * (256 >> 4), i16, acc);
   }
 }
@@ -106,7 +122,7 @@ attn_sw_fwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       const uint32_t tile = sel == 0 ? sQ : (sel == 1 ? sK : sV);
       const int tile_rows = sel == 0 ? kQB : TK;
       const int r0 = row_g + (sel == 0 ? q0 : blk * kQB);
-      const SwOp op = sw_op(tile, tile_rows, blk * kQB);
+      const SwOp op = sw_op(tile, tile_rows, blk * kQB, sw_row_bytes(DP));
       if (lane < kBoxes) tma_load_2d(&tm_a, ld_bar, smem + (op.a - sQ), (sel * H + h) * dh, r0);
       else tma_load_4d(&tm_b, ld_bar, op.b, 0, 0, ((sel * H + h) * dh) / 8 + 8, r0 / 8);
     }
@@ -127,7 +143,7 @@ attn_sw_fwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   const uint32_t tS = tmem, tO = tmem;
   if (tid == 0) {
     mbar_wait(ld_bar, 0);
-    sw_mma_kk<DP>(tS, sw_op(sQ, kQB, 0), sw_op(sK, TK, 0), TK);
+    sw_mma_kk<DP>(tS, sw_op(sQ, kQB, 0, sw_row_bytes(DP)), sw_op(sK, TK, 0, sw_row_bytes(DP)), TK);
     umma_commit(bar);
   }
   mbar_wait(bar, 0);
@@ -180,8 +196,8 @@ attn_sw_fwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     // O[128 x DP] = P[128 x TK] (K-major, no-swizzle) * V (split tile, contraction over the keys)
 #pragma unroll
     for (int kb = 0; kb < TK / kQB; ++kb)
-      sw_mma_tok<DP>(tO, make_smem_desc_nosw(sP + kb * (kQB / 8) * 128, 128, kPBlk), 256 >> 4, 0, sw_op(sV, TK, kb * kQB),
-                     kb > 0);
+      sw_mma_tok<DP>(tO, make_smem_desc_nosw(sP + kb * (kQB / 8) * 128, 128, kPBlk), 256 >> 4, 0,
+                     sw_op(sV, TK, kb * kQB, sw_row_bytes(DP)), kb > 0);
     umma_commit(bar);
   }
   if constexpr (kTPR == 2) l = s_red[2 * kQB + row] + s_red[3 * kQB + row];
@@ -416,7 +432,7 @@ static int launch_sw_fwd(const void* qkv, void* out, float* lse, int B, int T, i
   }
   alignas(64) CUtensorMap ta, tb;
   const unsigned long long rows = static_cast<unsigned long long>(B) * T, cols = 3ull * H * dh;
-  int rc = make_row_tile_tmap(&ta, qkv, rows, cols, 64, kQB);
+  int rc = make_row_tile_tmap(&ta, qkv, rows, cols, DP >= 64 ? 64 : DP, kQB);
   if (rc != MDT_OK) return rc;
   if (DP > 64) {
     rc = make_token_tile_tmap(&tb, qkv, rows, cols, 1, kQB / 8);
@@ -438,6 +454,10 @@ int attention_sw_fwd(const void* qkv, void* out, float* lse, int B, int T, int H
   } else if (dh == 64) {
     if (T == 128) return launch_sw_fwd<64, 128>(qkv, out, lse, B, T, H, dh, scale, st);
     if (T == 256) return launch_sw_fwd<64, 256>(qkv, out, lse, B, T, H, dh, scale, st);
+  } else if (dh == 32 && T == 256) {
+    // SWIZZLE_64B variant (decoder): written at the end of round 1 without GPU time left to validate it - opt-in
+    static const bool on = [] { const char* e = getenv("MDT_ATTN_SW64"); return e && e[0] == '1'; }();
+    if (on) return launch_sw_fwd<32, 256>(qkv, out, lse, B, T, H, dh, scale, st);
   }
   return MDT_ERR_UNSUPPORTED;
 }

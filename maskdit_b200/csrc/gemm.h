@@ -34,7 +34,8 @@ int gemm_launch(const mdt_gemm_args& a, cudaStream_t stream);
 // [row block][chunk][row % 8][16 B].  `m` is a CUtensorMap (opaque here to keep cuda.h out of this header).
 int make_token_tile_tmap(void* m, const void* ptr, unsigned long long rows, unsigned long long row_elems,
                          unsigned box_chunks, unsigned box_row_blocks);
-// 2-D bf16 tensor map of a row-major matrix [rows, row_elems], box {box_cols, box_rows}, SWIZZLE_128B (box_cols = 64).
+// 2-D bf16 tensor map of a row-major matrix [rows, row_elems], box {box_cols, box_rows}: SWIZZLE_128B for
+// box_cols = 64, SWIZZLE_64B for box_cols = 32.
 int make_row_tile_tmap(void* m, const void* ptr, unsigned long long rows, unsigned long long row_elems,
                        unsigned box_cols, unsigned box_rows);
 

@@ -544,8 +544,21 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t o
 
 int make_row_tile_tmap(void* m, const void* ptr, unsigned long long rows, unsigned long long row_elems,
                        unsigned box_cols, unsigned box_rows) {
-  if (box_cols != 64 || box_rows > 256 || (row_elems % 8) || (reinterpret_cast<uintptr_t>(ptr) & 15)) return MDT_ERR_ARG;
-  return make_tmap(static_cast<CUtensorMap*>(m), ptr, row_elems, rows, row_elems, box_cols, box_rows);
+  if ((box_cols != 64 && box_cols != 32) || box_rows > 256 || (row_elems % 8) || (reinterpret_cast<uintptr_t>(ptr) & 15))
+    return MDT_ERR_ARG;
+  if (box_cols == 64)
+    return make_tmap(static_cast<CUtensorMap*>(m), ptr, row_elems, rows, row_elems, box_cols, box_rows);
+  // 32 columns = 64-byte rows: SWIZZLE_64B
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return MDT_ERR_DRIVER;
+  cuuint64_t dims[2] = {row_elems, rows};
+  cuuint64_t strides[1] = {row_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(static_cast<CUtensorMap*>(m), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MDT_OK : MDT_ERR_TMAP;
 }
 
 int make_token_tile_tmap(void* m, const void* ptr, unsigned long long rows, unsigned long long row_elems,

@@ -363,8 +363,8 @@ int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const f
                      int H, int dh, float scale, cudaStream_t st);
 // attention_sw.cu: head_dim 64 / 72 with TMA-friendly split tiles (T = 128 / 256)
 int attention_sw_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale, cudaStream_t st);
-int attention_sw_bwd(const void* qkv, const void* dout, const float* lse, void* dqkv, int B, int T, int H, int dh,
-                     float scale, cudaStream_t st);
+int attention_sw_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int T,
+                     int H, int dh, float scale, cudaStream_t st);
 // attention_tc_long.cu: T = 512 / 1024 (and the T = 256 backward the persistent kernel does not cover)
 int attention_tc_long_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale,
                           cudaStream_t st);
@@ -444,7 +444,7 @@ int mdt_attention_bwd(const void* qkv, const void* out, const void* dout, const 
   float* delta = const_cast<float*>(lse) + static_cast<size_t>(B) * H * T;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_tc()) {
-    int rc = attention_sw_bwd(qkv, dout, lse, dqkv, B, T, H, dh, scale, st);
+    int rc = attention_sw_bwd(qkv, out, dout, lse, dqkv, B, T, H, dh, scale, st);
     if (rc != MDT_ERR_UNSUPPORTED) return rc;
     rc = attention_tc_bwd(qkv, out, dout, lse, dqkv, B, T, H, dh, scale, st);
     if (rc != MDT_ERR_UNSUPPORTED) return rc;

@@ -409,6 +409,222 @@ attn_sw_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// backward, T = 256, head_dim 32 (decoder): two query blocks x two key blocks per (b,h), persistent, one CTA per SM.
+// Same phase structure as attn_tc_bwd_kernel<32, 2> (attention_tc.cu) on SWIZZLE_64B tiles: 10 bulk loads per item
+// (Q, K, V, dO, O as [256 x 32] tiles), delta = rowsum(dO * O) read back from smem, dQ staged in the (dead) O tile,
+// dK / dV staged in the P region, 6 bulk stores per item.
+// NOT yet run on hardware (written after the round's GPU budget was spent): dispatched only with MDT_ATTN_SW64=1.
+// ------------------------------------------------------------------------------------------------------------
+// N fp32 values of row `row` -> bf16 chunks c8_0.. of a SWIZZLE_64B tile (64-byte rows, 4 chunks per row)
+template <int N>
+MDT_DEVINL void stage_row_sw64(uint32_t tile, int row, int c8_0, const uint32_t* r) {
+#pragma unroll
+  for (int g = 0; g < N / 8; ++g) {
+    const int c8 = c8_0 + g;
+    sts128u(tile + row * 64 + ((c8 ^ ((row >> 1) & 3)) << 4),
+            make_uint4(pack_bf16(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1])),
+                       pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3])),
+                       pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5])),
+                       pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]))));
+  }
+}
+
+__global__ void __launch_bounds__(kSwBwdThreads, 1)
+attn_sw_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                    const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_g,
+                    const float* __restrict__ lse, int H, float scale, int nitems) {
+  constexpr int DP = 32, NB = 2, T = NB * kQB;
+  constexpr int kPBlk = (kQB / 8) * 128;
+  constexpr uint32_t kRow = 64;                  // bytes per tile row
+  constexpr int kTileBytes = T * kRow;           // 16 KB
+  constexpr int kSetBytes = 5 * kTileBytes;      // Q | K | V | dO | O
+  constexpr int kOutTile = kQB * kRow;           // one staged 128-row gradient tile (8 KB)
+  static_assert(4 * kOutTile <= kQB * kQB * 2, "dK / dV tiles are staged in the P region");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t s0 = smem_u32(smem);
+  const uint32_t sP = s0 + 2 * kSetBytes, sdS = sP + kQB * kQB * 2;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * kSetBytes + 2 * kQB * kQB * 2);
+  uint64_t* ld_bar = bar + 1;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid & (kQB - 1), half = tid >> 7;
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(&ld_bar[0], 1);
+    mbar_init(&ld_bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  constexpr int kIoWarp = 7;
+  auto issue_loads = [&](int item, int set_idx) {  // 5 tiles x 2 boxes of 128 rows
+    if (warp != kIoWarp) return;
+    const uint32_t set = s0 + set_idx * kSetBytes;
+    const int b = item / H, h = item % H;
+    if (lane == 0) mbar_arrive_expect_tx(&ld_bar[set_idx], static_cast<uint32_t>(kSetBytes));
+    __syncwarp();
+    if (lane < 10) {
+      const int tile = lane >> 1, blk = lane & 1;
+      const uint32_t dst = set + tile * kTileBytes + blk * kOutTile;
+      const int col = (tile < 3 ? tile * H + h : h) * DP, r0 = b * T + blk * kQB;
+      const CUtensorMap* m = tile < 3 ? &tm_qkv : (tile == 3 ? &tm_do : &tm_o);
+      tma_load_2d(m, &ld_bar[set_idx], smem + (dst - s0), col, r0);
+    }
+  };
+  int item = blockIdx.x;
+  if (item < nitems) issue_loads(item, 0);
+  float lse_next[NB];
+#pragma unroll
+  for (int qb = 0; qb < NB; ++qb)
+    lse_next[qb] = item < nitems ? lse[static_cast<long long>(item) * T + qb * kQB + row] : 0.f;
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256, tKV = tmem + 256 + DP;  // dK[j] | dV[j] at tKV + j*2DP
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const float sl = scale * 1.4426950408889634f;
+  uint32_t phase = 0;
+
+  for (int it = 0; item < nitems; ++it, item += gridDim.x) {
+    const uint32_t set = s0 + (it & 1) * kSetBytes;
+    const uint32_t sQ = set, sK = set + kTileBytes, sV = set + 2 * kTileBytes, sdO = set + 3 * kTileBytes,
+                   sO = set + 4 * kTileBytes;
+    const int b = item / H, h = item % H;
+    const int nxt = item + gridDim.x;
+    float lse_all[NB];
+#pragma unroll
+    for (int qb = 0; qb < NB; ++qb) lse_all[qb] = lse_next[qb];
+    // The other set (tiles of item it-1, incl. the dQ tile staged in its O slot) and the P region are read by the bulk
+    // stores of item it-1: wait for those reads before the prefetch / the first P write may overwrite them.
+    if (warp == kIoWarp) bulk_wait_read_all();
+    if (nxt < nitems) {
+      issue_loads(nxt, (it + 1) & 1);
+#pragma unroll
+      for (int qb = 0; qb < NB; ++qb) lse_next[qb] = lse[static_cast<long long>(nxt) * T + qb * kQB + row];
+    }
+    mbar_wait(&ld_bar[it & 1], (it >> 1) & 1);
+    // delta_q = sum_d O[q,d] dO[q,d]: both tiles carry the same chunk permutation, so the row is read position-wise
+    float delta_all[NB];
+#pragma unroll
+    for (int qb = 0; qb < NB; ++qb) {
+      const uint32_t off = (qb * kQB + row) * kRow;
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 a, d;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(sO + off + c * 16));
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "r"(sdO + off + c * 16));
+        acc += bf16_lo(a.x) * bf16_lo(d.x) + bf16_hi(a.x) * bf16_hi(d.x) + bf16_lo(a.y) * bf16_lo(d.y) +
+               bf16_hi(a.y) * bf16_hi(d.y) + bf16_lo(a.z) * bf16_lo(d.z) + bf16_hi(a.z) * bf16_hi(d.z) +
+               bf16_lo(a.w) * bf16_lo(d.w) + bf16_hi(a.w) * bf16_hi(d.w);
+      }
+      delta_all[qb] = acc;
+    }
+    tcgen05_fence_before();
+    __syncthreads();  // every thread read O (its slot becomes the dQ staging tile) and the stores above have drained
+    if (tid == 0) {
+      tcgen05_fence_after();
+      sw_mma_kk<DP>(tS, sw_op(sQ, T, 0, kRow), sw_op(sK, T, 0, kRow), kQB);
+      sw_mma_kk<DP>(tdP, sw_op(sdO, T, 0, kRow), sw_op(sV, T, 0, kRow), kQB);
+      umma_commit(bar);
+    }
+#pragma unroll 1
+    for (int qb = 0; qb < NB; ++qb) {
+      const float delta = qb == 0 ? delta_all[0] : delta_all[NB - 1];
+      const float lsl = (qb == 0 ? lse_all[0] : lse_all[NB - 1]) * 1.4426950408889634f;
+#pragma unroll 1
+      for (int kb = 0; kb < NB; ++kb) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tcgen05_fence_after();
+        const uint32_t prow = (row >> 3) * kPBlk + (row & 7) * 16;
+#pragma unroll 1
+        for (int c = half * (kQB / 2); c < (half + 1) * (kQB / 2); c += 32) {
+          uint32_t rs_[32], rp[32];
+          tmem_ld_32x32b_x32(tS + lane_addr + c, rs_);
+          tmem_ld_32x32b_x32(tdP + lane_addr + c, rp);
+          tcgen05_wait_ld();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float p[8], ds[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              p[j] = fast_exp2(__uint_as_float(rs_[8 * g + j]) * sl - lsl);
+              ds[j] = p[j] * (__uint_as_float(rp[8 * g + j]) - delta) * scale;
+            }
+            const uint32_t o = prow + (c / 8 + g) * 128;
+            sts128u(sP + o, make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]),
+                                       pack_bf16(p[6], p[7])));
+            sts128u(sdS + o, make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]),
+                                        pack_bf16(ds[6], ds[7])));
+          }
+        }
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+          tcgen05_fence_after();
+          const uint32_t tdK = tKV + kb * 2 * DP, tdV = tdK + DP;
+          // dV[kb] += P^T dO[qb] ; dK[kb] += dS^T Q[qb] (contraction over the queries) ; dQ[qb] += dS K[kb] (over the keys)
+          sw_mma_tok<DP>(tdV, make_smem_desc_nosw(sP, kPBlk, 128), (2 * kPBlk) >> 4, 1, sw_op(sdO, T, qb * kQB, kRow), qb > 0);
+          sw_mma_tok<DP>(tdK, make_smem_desc_nosw(sdS, kPBlk, 128), (2 * kPBlk) >> 4, 1, sw_op(sQ, T, qb * kQB, kRow), qb > 0);
+          sw_mma_tok<DP>(tdQ, make_smem_desc_nosw(sdS, 128, kPBlk), 256 >> 4, 0, sw_op(sK, T, kb * kQB, kRow), kb > 0);
+          int nq = qb, nk = kb + 1;
+          if (nk == NB) nk = 0, ++nq;
+          if (nq < NB) {  // next (qb, kb): S and dP right away, one commit covers everything issued so far
+            sw_mma_kk<DP>(tS, sw_op(sQ, T, nq * kQB, kRow), sw_op(sK, T, nk * kQB, kRow), kQB);
+            sw_mma_kk<DP>(tdP, sw_op(sdO, T, nq * kQB, kRow), sw_op(sV, T, nk * kQB, kRow), kQB);
+          }
+          umma_commit(bar);
+        }
+      }
+      // dQ of this query block is complete once the last commit lands (the same commit also covers the next S/dP)
+      mbar_wait(bar, phase);
+      tcgen05_fence_after();
+      {
+        constexpr int HC = DP / 2;  // the two threads of a row take 16 columns each = chunks {0,1} / {2,3}
+        uint32_t r[HC];
+        tmem_ld_cols<HC>(tdQ + lane_addr + half * HC, r);
+        stage_row_sw64<HC>(sO, qb * kQB + row, half * (HC / 8), r);
+      }
+      // the next iteration's first wait uses the same (already completed) phase: do not flip here
+      tcgen05_fence_before();
+      __syncthreads();  // all rows read dQ before the next query block's MMAs (queued behind this commit) reuse it
+    }
+    phase ^= 1;  // the last commit of the item has been consumed by the wait above
+    // dK / dV: rows = keys; threads 0-127 stage dK, threads 128-255 stage dV: tile (kb, half) in the P region
+#pragma unroll 1
+    for (int kb = 0; kb < NB; ++kb) {
+      uint32_t r[DP];
+      tmem_ld_cols<DP>(tKV + kb * 2 * DP + half * DP + lane_addr, r);
+      stage_row_sw64<DP>(sP + (kb * 2 + half) * kOutTile, row, 0, r);
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();  // accumulators and tiles of this item are dead; the next item may overwrite them
+    tcgen05_fence_after();
+    if (warp == kIoWarp) {
+      if (lane < 6) {  // dQ blocks 0/1 from the O slot, then (dK, dV) of key blocks 0/1 from the P region
+        const int sel = lane < 2 ? 0 : 1 + ((lane - 2) & 1), blk = lane < 2 ? lane : (lane - 2) >> 1;
+        const uint32_t src = lane < 2 ? sO + blk * kOutTile : sP + (blk * 2 + (sel - 1)) * kOutTile;
+        tma_store_2d(&tm_g, src, (sel * H + h) * DP, b * T + blk * kQB);
+      }
+      bulk_commit_group();
+    }
+  }
+  if (warp == kIoWarp) bulk_wait_all();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------------------
 static bool attn_sw() {  // MDT_ATTN_SW=0: the no-swizzle kernels of attention_tc.cu (A/B switch)
@@ -498,11 +714,46 @@ static int launch_sw_bwd(const void* qkv, const void* dout, const float* lse, vo
   return cudaGetLastError() == cudaSuccess ? MDT_OK : MDT_ERR_CUDA;
 }
 
-int attention_sw_bwd(const void* qkv, const void* dout, const float* lse, void* dqkv, int B, int T, int H, int dh,
+static int launch_sw_bwd2(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B,
+                          int H, float scale, cudaStream_t st) {
+  constexpr int T = 2 * kQB, DP = 32;
+  const int smem = 2 * 5 * T * 64 + 2 * kQB * kQB * 2 + 64 + 1024;
+  static bool set = false;
+  static int sms = 0;
+  if (!set) {
+    if (cudaFuncSetAttribute(attn_sw_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return MDT_ERR_CUDA;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    set = true;
+  }
+  alignas(64) CUtensorMap tm[4];
+  const unsigned long long rows = static_cast<unsigned long long>(B) * T;
+  const void* ptrs[4] = {qkv, dout, out, dqkv};
+  const unsigned long long cols[4] = {3ull * H * DP, 1ull * H * DP, 1ull * H * DP, 3ull * H * DP};
+  for (int i = 0; i < 4; ++i) {
+    const int rc = make_row_tile_tmap(&tm[i], ptrs[i], rows, cols[i], DP, kQB);
+    if (rc != MDT_OK) return rc;
+  }
+  const int nitems = B * H;
+  attn_sw_bwd2_kernel<<<nitems < sms ? nitems : sms, kSwBwdThreads, smem, st>>>(tm[0], tm[1], tm[2], tm[3], lse, H,
+                                                                                scale, nitems);
+  return cudaGetLastError() == cudaSuccess ? MDT_OK : MDT_ERR_CUDA;
+}
+
+int attention_sw_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int T, int H, int dh,
                      float scale, cudaStream_t st) {
-  if (!attn_sw() || T != kQB) return MDT_ERR_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dqkv)) & 15)
+  if (!attn_sw()) return MDT_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dqkv) |
+       reinterpret_cast<uintptr_t>(out)) & 15)
     return MDT_ERR_UNSUPPORTED;
+  if (T == 2 * kQB && dh == 32) {  // decoder: SWIZZLE_64B tiles, opt-in until it has been run on hardware
+    static const bool on = [] { const char* e = getenv("MDT_ATTN_SW64"); return e && e[0] == '1'; }();
+    return on ? launch_sw_bwd2(qkv, out, dout, lse, dqkv, B, H, scale, st) : MDT_ERR_UNSUPPORTED;
+  }
+  if (T != kQB) return MDT_ERR_UNSUPPORTED;
   if (dh == 72) return launch_sw_bwd<80>(qkv, dout, lse, dqkv, B, H, dh, scale, st);
   if (dh == 64) return launch_sw_bwd<64>(qkv, dout, lse, dqkv, B, H, dh, scale, st);
   return MDT_ERR_UNSUPPORTED;

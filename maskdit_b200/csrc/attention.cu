@@ -365,6 +365,11 @@ int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const f
 int attention_sw_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale, cudaStream_t st);
 int attention_sw_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int T,
                      int H, int dh, float scale, cudaStream_t st);
+// attention_sw_long.cu: the blocked kernels on split TMA tiles (opt-in, MDT_ATTN_SWL=1)
+int attention_sw_long_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale,
+                          cudaStream_t st);
+int attention_sw_long_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
+                          void* dqkv, int B, int T, int H, int dh, float scale, cudaStream_t st);
 // attention_tc_long.cu: T = 512 / 1024 (and the T = 256 backward the persistent kernel does not cover)
 int attention_tc_long_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale,
                           cudaStream_t st);
@@ -423,6 +428,8 @@ int mdt_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int 
     rc = attention_tc_fwd(qkv, out, lse, B, T, H, dh, scale, static_cast<cudaStream_t>(stream));
     if (rc != MDT_ERR_UNSUPPORTED) return rc;
     if (use_tc_long()) {
+      rc = attention_sw_long_fwd(qkv, out, lse, B, T, H, dh, scale, static_cast<cudaStream_t>(stream));
+      if (rc != MDT_ERR_UNSUPPORTED) return rc;
       rc = attention_tc_long_fwd(qkv, out, lse, B, T, H, dh, scale, static_cast<cudaStream_t>(stream));
       if (rc != MDT_ERR_UNSUPPORTED) return rc;
     }
@@ -449,6 +456,8 @@ int mdt_attention_bwd(const void* qkv, const void* out, const void* dout, const 
     rc = attention_tc_bwd(qkv, out, dout, lse, dqkv, B, T, H, dh, scale, st);
     if (rc != MDT_ERR_UNSUPPORTED) return rc;
     if (use_tc_long()) {
+      rc = attention_sw_long_bwd(qkv, out, dout, lse, delta, dqkv, B, T, H, dh, scale, st);
+      if (rc != MDT_ERR_UNSUPPORTED) return rc;
       rc = attention_tc_long_bwd(qkv, out, dout, lse, delta, dqkv, B, T, H, dh, scale, st);
       if (rc != MDT_ERR_UNSUPPORTED) return rc;
     }

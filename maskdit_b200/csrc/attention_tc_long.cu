@@ -187,6 +187,13 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
   }
 }
 
+// delta pre-kernel launch (also used by attention_sw_long.cu)
+void launch_attn_delta(const void* out, const void* dout, float* delta, int B, int T, int H, int dh, cudaStream_t st) {
+  const long long n = static_cast<long long>(B) * T * H;
+  attn_delta_kernel<<<static_cast<int>((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), delta, B, T, H, dh);
+}
+
 // P / dS of this thread's half row from the S / dP accumulators; writes sdS (and sP if WRITE_P)
 template <bool WRITE_P>
 MDT_DEVINL void softmax_bwd_half(uint32_t tS, uint32_t tdP, uint32_t lane_addr, int half, int row, uint32_t sP,
@@ -459,9 +466,7 @@ static int launch_long_bwd(const void* qkv, const void* out, const void* dout, c
     if (int rc = set_smem(k_dkv, smem_dkv)) return rc;
     set = true;
   }
-  const long long n = static_cast<long long>(B) * T * H;
-  attn_delta_kernel<<<static_cast<int>((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16), 256, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), delta, B, T, H, dh);
+  launch_attn_delta(out, dout, delta, B, T, H, dh, st);
   k_dq<<<dim3(NB, B * H), kLT, smem_dq, st>>>(static_cast<const __nv_bfloat16*>(qkv),
                                               static_cast<const __nv_bfloat16*>(dout), lse, delta,
                                               static_cast<__nv_bfloat16*>(dqkv), H, dh, scale);

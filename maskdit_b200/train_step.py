@@ -72,7 +72,7 @@ def ar_chunk_bounds(n, k):
 class TrainStep:
     def __init__(self, net: EDMPrecond, ema: EDMPrecond | None = None, lr=1e-4, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=0.0, ema_decay=0.9999, loss_fn: EDMLoss | None = None, process_group=None,
-                 lr_rampup_kimg=0.0, global_batch=None, device=None, overlap=False):
+                 lr_rampup_kimg=0.0, global_batch=None, device=None, overlap=False, graph=None):
         self.net, self.ema = net, ema
         self.lr, self.betas, self.eps, self.wd, self.ema_decay = lr, betas, eps, weight_decay, ema_decay
         self.loss_fn = loss_fn or EDMLoss()
@@ -95,6 +95,8 @@ class TrainStep:
                 p.grad = self.st.gview(k)
         # Overlap: gradient ranges are reduced + stepped on a side stream as soon as a block's backward is enqueued.
         self.overlap = overlap
+        self.graph = (os.environ.get("MDT_TRAIN_GRAPH", "0") == "1") if graph is None else bool(graph)
+        self._graphs = {}
         self.bg_blocks = 24
         # gradient all-reduce in this many chunks, pipelined against the optimizer pass (world > 1).  Default 1 = one
         # flat call: measured on 2 x B200 (same box) 132.0 ms/step flat vs 133.3 ms with 8 chunks - the all-reduce and
@@ -164,16 +166,53 @@ class TrainStep:
             self._reduce_and_step(lo, hi, max_blocks=self.bg_blocks)
         self._done.append((lo, hi))
 
+    def _fwd_bwd_graphed(self, images, labels, mask_ratio, mae_loss_coef):
+        """Gradient zeroing + loss forward + engine backward (~770 launches, 70 ms of host time) replayed from a CUDA
+        graph captured once per (shapes, mask_ratio, mae_loss_coef); the all-reduce and the optimizer pass stay eager
+        (their scalars change every step).  Opt-in (`TrainStep(graph=True)` / MDT_TRAIN_GRAPH=1): written at the end of
+        round 1 and NOT yet run on hardware."""
+        key = (tuple(images.shape), tuple(labels.shape), float(mask_ratio), float(mae_loss_coef))
+        ent = self._graphs.get(key)
+        if ent is None:
+            gx, gy = images.clone(), labels.clone()
+
+            def body():
+                self.st.grad.zero_()
+                loss = self.loss_fn(self.net, gx, gy, mask_ratio=mask_ratio, mae_loss_coef=mae_loss_coef)
+                loss.mean().backward()
+                return loss.detach()
+
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):   # warm-up outside the capture (lazy kernel attributes, allocator pools)
+                body()
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.L.LAUNCHES
+            with torch.cuda.graph(graph):
+                out = body()
+            ent = (graph, gx, gy, out, ops.L.LAUNCHES - n0)
+            self._graphs[key] = ent
+        graph, gx, gy, out, n_launch = ent
+        gx.copy_(images), gy.copy_(labels)
+        graph.replay()
+        ops.L.LAUNCHES += n_launch
+        return out.clone()
+
     def step(self, images, labels, mask_ratio=0.5, mae_loss_coef=0.1):
         """One optimisation step on this rank's shard.  Returns the per-sample loss [B] (device tensor)."""
         st = self.st
-        st.grad.zero_()
         self.step_count += 1
         gb = self.global_batch or images.shape[0] * self.world
         self._lr_now = lr_at(self.step_count, self.lr, gb, self.rampup) if self.rampup > 0 else self.lr
         self._done = []
-        loss = self.loss_fn(self.net, images, labels, mask_ratio=mask_ratio, mae_loss_coef=mae_loss_coef)
-        loss.mean().backward()   # engine backward; with overlap=True block ranges are already being reduced/stepped
+        if self.graph and not self.overlap and ops.L.GEMM_PROFILE is None:
+            loss = self._fwd_bwd_graphed(images, labels, mask_ratio, mae_loss_coef)
+        else:
+            st.grad.zero_()
+            loss = self.loss_fn(self.net, images, labels, mask_ratio=mask_ratio, mae_loss_coef=mae_loss_coef)
+            loss.mean().backward()   # engine backward; with overlap=True block ranges are already being reduced/stepped
         main = torch.cuda.current_stream()
         if self.overlap:
             self.side.wait_stream(main)

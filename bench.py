@@ -296,9 +296,9 @@ def bench_train(args, net, dev, world, rank, R, PK, sync_all, max_over_ranks):
                      "step_achieved": sps / world * flop / 1e12, "step_frac": sps / world * flop / 1e12 / PK["sustained"]},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb, secs = cpu_reference_train(2, 2, 1, R=R)
+        cb, secs = cpu_reference_train(2, 4, 1, R=R)
         line["cpu_baseline"] = {"value": cb, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"2 timed steps (+1 warm-up) of batch 2, fwd+bwd+AdamW, torch CPU fp32, "
+                                "sample": f"4 timed steps (+1 warm-up) of batch 2, fwd+bwd+AdamW, torch CPU fp32, "
                                           f"{torch.get_num_threads()} threads ({secs:.1f} s)"}
     return line
 

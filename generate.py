@@ -3,8 +3,12 @@
 
 Builds `Precond_models[config.model.precond]` from the YAML, loads `ckpt['ema']` (reference checkpoints load
 unchanged: same state-dict keys), and runs `edm_sampler` on the B200 engine for the requested seeds with
-per-sample generators (utils.StackedRandomGenerator, utils.py:119-133).  The SD-VAE decode + PNG writing of the
-reference (sample.py:275-296) is outside the accelerated path: latents are saved as `.npy` per seed.
+per-sample generators (utils.StackedRandomGenerator, utils.py:119-133).  Under torchrun the seed batches are dealt
+to the ranks exactly as generate_with_net does (sample.py:232-235: rank-strided, one barrier per batch); giving any of
+--solver / --discretization / --schedule / --scaling selects `ablation_sampler` (sample.py:243-245).  The SD-VAE
+decode of the reference (sample.py:275, a separate convolutional network) is outside the accelerated path (SURVEY.md
+§2): latents are saved as `.npy` per seed; the 8-bit conversion + PNG writing of sample.py:287-296 exist
+(`ops.to_uint8_nhwc`, `sampler.write_png`) and `--png_preview` applies them to the raw latent channels.
 """
 import argparse
 import os
@@ -13,7 +17,8 @@ import numpy as np
 import torch
 
 from maskdit_b200.config import build_net, load_config, parse_float_none, parse_int_list
-from maskdit_b200.sampler import edm_sampler
+from maskdit_b200 import ops
+from maskdit_b200.sampler import ablation_sampler, edm_sampler, rank_seed_batches, write_png
 
 
 class StackedRandomGenerator:
@@ -41,17 +46,35 @@ def main():
     ap.add_argument("--num_steps", type=int, default=40)
     ap.add_argument("--S_churn", type=int, default=0)
     ap.add_argument("--max_batch_size", type=int, default=32)
+    # ablation_sampler switches (sample.py:358-364): giving any of them selects the generalised sampler
+    ap.add_argument("--solver", choices=["euler", "heun"], default=None)
+    ap.add_argument("--discretization", choices=["vp", "ve", "iddpm", "edm"], default=None)
+    ap.add_argument("--schedule", choices=["vp", "ve", "linear"], default=None)
+    ap.add_argument("--scaling", choices=["vp", "none"], default=None)
+    ap.add_argument("--png_preview", action="store_true",
+                    help="also write channels 0-2 of every latent as an 8-bit PNG (no SD-VAE in this repo)")
     args, _ = ap.parse_known_args()
     cfg = load_config(args.config)
-    device = torch.device("cuda")
+    rank, size = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if size > 1:
+        torch.distributed.init_process_group("nccl", device_id=device)
     net = build_net(cfg).to(device).eval()
     if args.ckpt_path:
-        ck = torch.load(args.ckpt_path, map_location=device)
+        # trusted checkpoint: reference checkpoints hold an argparse.Namespace under 'args' (train.py:259-265)
+        ck = torch.load(args.ckpt_path, map_location=device, weights_only=False)
         net.load_state_dict({k.replace("_orig_mod.", ""): v for k, v in ck["ema"].items()})
     os.makedirs(args.results_dir, exist_ok=True)
-    seeds = args.seeds
-    for i in range(0, len(seeds), args.max_batch_size):
-        bs = seeds[i:i + args.max_batch_size]
+    kw = {k: getattr(args, k) for k in ("solver", "discretization", "schedule", "scaling") if getattr(args, k)}
+    sampler_fn = ablation_sampler if kw else edm_sampler          # sample.py:243-245
+    n_done = 0
+    for bs in rank_seed_batches(args.seeds, args.max_batch_size, rank, size):   # sample.py:232-235: rank-strided
+        if size > 1:
+            torch.distributed.barrier()                          # sample.py:253
+        if not bs:
+            continue
         rnd = StackedRandomGenerator(device, bs)
         latents = rnd.randn([len(bs), net.img_channels, net.img_resolution, net.img_resolution], device=device)
         labels = torch.eye(net.num_classes, device=device)[rnd.randint(net.num_classes, size=[len(bs)], device=device)]
@@ -59,11 +82,18 @@ def main():
             labels[:, :] = 0
             labels[:, args.class_idx] = 1
         with torch.no_grad():
-            z = edm_sampler(net, latents.float(), labels.float(), cfg_scale=args.cfg_scale,
-                            randn_like=rnd.randn_like, num_steps=args.num_steps, S_churn=args.S_churn).float()
+            z = sampler_fn(net, latents.float(), labels.float(), cfg_scale=args.cfg_scale,
+                           randn_like=rnd.randn_like, num_steps=args.num_steps, S_churn=args.S_churn, **kw).float()
+        if args.png_preview:
+            px = ops.to_uint8_nhwc((z[:, :3] / z[:, :3].abs().amax().clamp_min(1e-8)).contiguous()).cpu().numpy()
+            for s, im in zip(bs, px):
+                write_png(os.path.join(args.results_dir, f"{s:06d}.png"), im)
         for s, zi in zip(bs, z.cpu().numpy()):
             np.save(os.path.join(args.results_dir, f"{s:06d}.npy"), zi)
-    print(f"wrote {len(seeds)} latents to {args.results_dir}")
+        n_done += len(bs)
+    print(f"rank {rank}: wrote {n_done} latents to {args.results_dir}")
+    if size > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

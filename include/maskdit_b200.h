@@ -27,6 +27,8 @@ extern "C" {
 
 const char* mdt_status_string(int status);
 int mdt_abi_version(void);
+/* BLOCK_N * 10 + CTAs-per-tile (1 or 2 = tcgen05 cta_group::2 SM pair) of the last mdt_gemm_bf16 launch (tests). */
+int mdt_gemm_last_config(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * bf16 tensor-core GEMM (tcgen05 / TMEM / TMA):  out[M,N] (+)= sum_k A[m,k] * B[n,k], fp32 accumulate.
@@ -139,6 +141,13 @@ int mdt_ln_modulate_bwd_gate(const void* dxmod_bf16, const float* x, const float
 int mdt_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, void* stream);
 int mdt_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int T,
                       int H, int dh, void* stream);
+/* Introspection for the parity tests (host-side, no launch): which kernel family served the last successful
+ * mdt_attention_fwd (which = 0) / mdt_attention_bwd (which = 1) call of this process:
+ *   0 mma.sync fallback (odd sequence lengths), 1 split-tile TMA tcgen05 (T = 128/256), 2 no-swizzle tcgen05,
+ *   3 blocked split-tile tcgen05 (T = 512/1024, T = 256 backward), 4 blocked no-swizzle tcgen05; -1 = none yet.
+ * With MDT_ATTN_STRICT=1 in the environment a shape no tcgen05 kernel accepts returns MDT_ERR_UNSUPPORTED instead
+ * of running the mma.sync kernels.                                                                             */
+int mdt_attention_last_impl(int which);
 
 /* ------------------------------------------------------------------------------------------------------------
  * unmask_tokens + decoder_pos_embed (models/maskdit.py:157-163,543-545):
@@ -163,6 +172,15 @@ int mdt_unmask_tokens_bwd(const float* g, const int64_t* ids_keep, const int64_t
 int mdt_edm_loss(const float* F, const float* xin, const float* y, const float* sigma, const float* mask,
                  const float* gl, float sigma_data, float mae_coef, float* loss, float* Dx, void* dF_bf16, int B,
                  int C, int R, int p, void* stream);
+/* Step front (train.py:206,209 + train_utils/loss.py:35-39 + utils.py:59-65) in one pass, given pre-drawn randoms:
+ *   y  = scale_factor * (mean + exp(0.5 * clamp(logvar, -30, 20)) * eps)   moments [B,2C,R,R] = (mean | logvar)
+ *   sigma[b] = exp(P_std * rnd_normal[b] + P_mean) ;  yn = y + noise_unit * sigma[b]
+ *   labels[b,:] = 0 where !(drop_u[b] >= drop_prob)   (labels / drop_u may be NULL: no label dropout)
+ * eps, noise_unit, y, yn: [B,C,R,R] f32 ; rnd_normal, drop_u, sigma: [B] f32 ; labels [B,num_classes] f32 in place. */
+int mdt_step_front(const float* moments, const float* eps, const float* rnd_normal, const float* noise_unit,
+                   const float* drop_u, float drop_prob, float scale_factor, float P_mean, float P_std, float* y,
+                   float* yn, float* sigma, float* labels, int B, int C, int R, int num_classes, void* stream);
+
 /* D only (sampler / generic autograd path): Dx = c_skip*xin + c_out*unpatchify(F); and its backward
  * dF_bf16 = c_out * patchify(gD).                                                                            */
 int mdt_edm_precond_out(const float* F, const float* xin, const float* sigma, float sigma_data, float* Dx, int B,
@@ -180,6 +198,16 @@ int mdt_cfg_precond_out(const float* F, const float* xin, const float* sigma, fl
  *   mode 1 (Heun):   d_prime = (x_next - den)/t_next ; x_next = x_hat + (t_next - t_hat)(0.5 d_cur + 0.5 d_prime) */
 int mdt_heun_update(int mode, const double* x_hat, const float* denoised, double* d_cur, double* x_next,
                     float* x_next_f32, double t_hat, double t_next, long long n, void* stream);
+
+/* Generalised fp64 sampler update for ablation_sampler (sample.py:73-188; Euler / Heun / churn steps of every
+ * discretization, schedule and scaling are linear combinations with host-computed fp64 scalars):
+ *   out = a*x + b*y + c*z (x, y fp64; z fp32 network output; y / z may be NULL) ; out_f32 = float(out * f32_scale)
+ *   (out or out_f32 may be NULL).                                                                                */
+int mdt_lincomb_f64(double a, const double* x, double b, const double* y, double c, const float* z, double* out,
+                    float* out_f32, double f32_scale, long long n, void* stream);
+
+/* Sampler tail (sample.py:287): img [B,C,H,W] f32 in [-1,1] -> uint8 [B,H,W,C] = clamp((img + 1) * 127.5, 0, 255).  */
+int mdt_to_uint8_nhwc(const float* img, unsigned char* out, int B, int C, int H, int W, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused AdamW (weight_decay handled as adam_w_mode, train.py:141) + EMA (train_utils/helper.py:47-58) + bf16

@@ -60,13 +60,18 @@ _SIGS = {
     "mdt_ln_modulate_bwd_gate": [_P, _P, _P, _P, _P, _I, _I, _P, _I, _P, _P, _I, _P, _P, _I, _P, _P, _I, _P, _I, _I, _P],
     "mdt_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _P],
     "mdt_attention_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mdt_attention_last_impl": [_I],
+    "mdt_gemm_last_config": [],
     "mdt_unmask_tokens": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mdt_unmask_tokens_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mdt_edm_loss": [_P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mdt_step_front": [_P, _P, _P, _P, _P, _F, _F, _F, _F, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mdt_edm_precond_out": [_P, _P, _P, _F, _P, _I, _I, _I, _I, _P],
     "mdt_edm_precond_out_bwd": [_P, _P, _F, _P, _I, _I, _I, _I, _P],
     "mdt_cfg_precond_out": [_P, _P, _P, _F, _F, _P, _I, _I, _I, _I, _P],
     "mdt_heun_update": [_I, _P, _P, _P, _P, _P, _D, _D, _LL, _P],
+    "mdt_lincomb_f64": [_D, _P, _D, _P, _D, _P, _P, _P, _D, _LL, _P],
+    "mdt_to_uint8_nhwc": [_P, _P, _I, _I, _I, _I, _P],
     "mdt_adamw_ema": [_P, _P, _P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _F, _I, _P],
 }
 

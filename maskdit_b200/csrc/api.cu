@@ -1,6 +1,8 @@
 // extern "C" surface that is not tied to one kernel file: status strings, ABI version, GEMM entry.
 #include "gemm.h"
 
+namespace mdt { extern int g_gemm_last_config; }
+
 extern "C" {
 
 const char* mdt_status_string(int status) {
@@ -16,6 +18,8 @@ const char* mdt_status_string(int status) {
 }
 
 int mdt_abi_version(void) { return 1; }
+
+int mdt_gemm_last_config(void) { return mdt::g_gemm_last_config; }
 
 int mdt_gemm_bf16(const mdt_gemm_args* args, void* stream) {
   if (!args || !args->A || !args->B || !args->out) return MDT_ERR_ARG;

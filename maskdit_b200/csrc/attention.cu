@@ -365,7 +365,7 @@ int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const f
 int attention_sw_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale, cudaStream_t st);
 int attention_sw_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int T,
                      int H, int dh, float scale, cudaStream_t st);
-// attention_sw_long.cu: the blocked kernels on split TMA tiles (opt-in, MDT_ATTN_SWL=1)
+// attention_sw_long.cu: the blocked kernels on split TMA tiles (default; MDT_ATTN_SWL=0 = attention_tc_long.cu)
 int attention_sw_long_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, float scale,
                           cudaStream_t st);
 int attention_sw_long_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
@@ -413,7 +413,27 @@ static int dp_of(int dh) {
     default: return MDT_ERR_UNSUPPORTED;                        \
   }
 
+// Which implementation served the last call (tests assert the production kernels ran instead of trusting the
+// fallthrough chain): 0 = mma.sync (attention.cu), 1 = split-tile TMA tcgen05 (attention_sw.cu), 2 = no-swizzle
+// tcgen05 (attention_tc.cu), 3 = blocked split-tile tcgen05 (attention_sw_long.cu), 4 = blocked no-swizzle tcgen05
+// (attention_tc_long.cu).  MDT_ATTN_STRICT=1: a shape none of the tcgen05 paths accepts is an error, not a fallback.
+static int g_attn_last_impl[2] = {-1, -1};
+static bool attn_strict() {
+  static const bool on = [] { const char* e = getenv("MDT_ATTN_STRICT"); return e && e[0] == '1'; }();
+  return on;
+}
+#define MDT_ATTN_TRY(WHICH, IMPL, CALL)                                  \
+  {                                                                      \
+    const int rc_ = (CALL);                                              \
+    if (rc_ != MDT_ERR_UNSUPPORTED) {                                    \
+      if (rc_ == MDT_OK) g_attn_last_impl[WHICH] = IMPL;                 \
+      return rc_;                                                        \
+    }                                                                    \
+  }
+
 extern "C" {
+
+int mdt_attention_last_impl(int which) { return (which == 0 || which == 1) ? g_attn_last_impl[which] : -1; }
 
 int mdt_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, void* stream) {
   if (!qkv || !out || B <= 0 || T <= 0 || H <= 0) return MDT_ERR_ARG;
@@ -423,17 +443,16 @@ int mdt_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int 
   dim3 grid((T + kTile - 1) / kTile, B * H);
   const float scale = 1.f / sqrtf(static_cast<float>(dh));
   if (use_tc()) {
-    int rc = attention_sw_fwd(qkv, out, lse, B, T, H, dh, scale, static_cast<cudaStream_t>(stream));
-    if (rc != MDT_ERR_UNSUPPORTED) return rc;
-    rc = attention_tc_fwd(qkv, out, lse, B, T, H, dh, scale, static_cast<cudaStream_t>(stream));
-    if (rc != MDT_ERR_UNSUPPORTED) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MDT_ATTN_TRY(0, 1, attention_sw_fwd(qkv, out, lse, B, T, H, dh, scale, st));
+    MDT_ATTN_TRY(0, 2, attention_tc_fwd(qkv, out, lse, B, T, H, dh, scale, st));
     if (use_tc_long()) {
-      rc = attention_sw_long_fwd(qkv, out, lse, B, T, H, dh, scale, static_cast<cudaStream_t>(stream));
-      if (rc != MDT_ERR_UNSUPPORTED) return rc;
-      rc = attention_tc_long_fwd(qkv, out, lse, B, T, H, dh, scale, static_cast<cudaStream_t>(stream));
-      if (rc != MDT_ERR_UNSUPPORTED) return rc;
+      MDT_ATTN_TRY(0, 3, attention_sw_long_fwd(qkv, out, lse, B, T, H, dh, scale, st));
+      MDT_ATTN_TRY(0, 4, attention_tc_long_fwd(qkv, out, lse, B, T, H, dh, scale, st));
     }
+    if (attn_strict()) return MDT_ERR_UNSUPPORTED;
   }
+  g_attn_last_impl[0] = 0;
   MDT_DP_DISPATCH(dp, attn_fwd_kernel<kDP><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
                           static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, T, H, dh,
                           scale));
@@ -451,17 +470,15 @@ int mdt_attention_bwd(const void* qkv, const void* out, const void* dout, const 
   float* delta = const_cast<float*>(lse) + static_cast<size_t>(B) * H * T;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_tc()) {
-    int rc = attention_sw_bwd(qkv, out, dout, lse, dqkv, B, T, H, dh, scale, st);
-    if (rc != MDT_ERR_UNSUPPORTED) return rc;
-    rc = attention_tc_bwd(qkv, out, dout, lse, dqkv, B, T, H, dh, scale, st);
-    if (rc != MDT_ERR_UNSUPPORTED) return rc;
+    MDT_ATTN_TRY(1, 1, attention_sw_bwd(qkv, out, dout, lse, dqkv, B, T, H, dh, scale, st));
+    MDT_ATTN_TRY(1, 2, attention_tc_bwd(qkv, out, dout, lse, dqkv, B, T, H, dh, scale, st));
     if (use_tc_long()) {
-      rc = attention_sw_long_bwd(qkv, out, dout, lse, delta, dqkv, B, T, H, dh, scale, st);
-      if (rc != MDT_ERR_UNSUPPORTED) return rc;
-      rc = attention_tc_long_bwd(qkv, out, dout, lse, delta, dqkv, B, T, H, dh, scale, st);
-      if (rc != MDT_ERR_UNSUPPORTED) return rc;
+      MDT_ATTN_TRY(1, 3, attention_sw_long_bwd(qkv, out, dout, lse, delta, dqkv, B, T, H, dh, scale, st));
+      MDT_ATTN_TRY(1, 4, attention_tc_long_bwd(qkv, out, dout, lse, delta, dqkv, B, T, H, dh, scale, st));
     }
+    if (attn_strict()) return MDT_ERR_UNSUPPORTED;
   }
+  g_attn_last_impl[1] = 0;
   MDT_DP_DISPATCH(dp, {
     attn_bwd_dq_kernel<kDP><<<grid, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv),
                                                   static_cast<const __nv_bfloat16*>(out),

@@ -344,7 +344,7 @@ attn_sw_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid_co
 // Same phase structure as attn_tc_bwd_kernel<32, 2> (attention_tc.cu) on SWIZZLE_64B tiles: 10 bulk loads per item
 // (Q, K, V, dO, O as [256 x 32] tiles), delta = rowsum(dO * O) read back from smem, dQ staged in the (dead) O tile,
 // dK / dV staged in the P region, 6 bulk stores per item.
-// NOT yet run on hardware (written after the round's GPU budget was spent): dispatched only with MDT_ATTN_SW64=1.
+// Default since round 2 (parity + timing on B200: profiles/r02_attention_paths.md); MDT_ATTN_SW64=0 disables.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSwBwdThreads, 1)
 attn_sw_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
@@ -588,8 +588,9 @@ int attention_sw_fwd(const void* qkv, void* out, float* lse, int B, int T, int H
     if (T == 128) return launch_sw_fwd<64, 128>(qkv, out, lse, B, T, H, dh, scale, st);
     if (T == 256) return launch_sw_fwd<64, 256>(qkv, out, lse, B, T, H, dh, scale, st);
   } else if (dh == 32 && T == 256) {
-    // SWIZZLE_64B variant (decoder): written at the end of round 1 without GPU time left to validate it - opt-in
-    static const bool on = [] { const char* e = getenv("MDT_ATTN_SW64"); return e && e[0] == '1'; }();
+    // SWIZZLE_64B variant (decoder).  Round 2, B200: parity green, 165 us vs 200 us for the 16-byte tile fills of
+    // attention_tc.cu at B=256 (profiles/r02_attention_paths.md); MDT_ATTN_SW64=0 switches back (A/B).
+    static const bool on = [] { const char* e = getenv("MDT_ATTN_SW64"); return !(e && e[0] == '0'); }();
     if (on) return launch_sw_fwd<32, 256>(qkv, out, lse, B, T, H, dh, scale, st);
   }
   return MDT_ERR_UNSUPPORTED;
@@ -666,8 +667,8 @@ int attention_sw_bwd(const void* qkv, const void* out, const void* dout, const f
   if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dqkv) |
        reinterpret_cast<uintptr_t>(out)) & 15)
     return MDT_ERR_UNSUPPORTED;
-  if (T == 2 * kQB && dh == 32) {  // decoder: SWIZZLE_64B tiles, opt-in until it has been run on hardware
-    static const bool on = [] { const char* e = getenv("MDT_ATTN_SW64"); return e && e[0] == '1'; }();
+  if (T == 2 * kQB && dh == 32) {  // decoder: SWIZZLE_64B tiles (292 us vs 338 us at B=256); MDT_ATTN_SW64=0 = A/B
+    static const bool on = [] { const char* e = getenv("MDT_ATTN_SW64"); return !(e && e[0] == '0'); }();
     return on ? launch_sw_bwd2(qkv, out, dout, lse, dqkv, B, H, scale, st) : MDT_ERR_UNSUPPORTED;
   }
   if (T != kQB) return MDT_ERR_UNSUPPORTED;

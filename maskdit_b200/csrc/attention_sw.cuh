@@ -15,7 +15,7 @@ struct SwOp {
   uint32_t plane;  // bytes between the two planes of block B (= 16 * rows of the whole tile)
 };
 // Block A holds min(DP, 64) columns: 128-byte rows in SWIZZLE_128B atoms for head_dim 64 / 72, 64-byte rows in
-// SWIZZLE_64B atoms for head_dim 32 (decoder; NOT yet validated on hardware: dispatched only with MDT_ATTN_SW64=1).
+// SWIZZLE_64B atoms for head_dim 32 (decoder; default since round 2, MDT_ATTN_SW64=0 disables).
 constexpr int sw_row_bytes(int dp) { return dp >= 64 ? 128 : dp * 2; }
 MDT_DEVINL SwOp sw_op(uint32_t tile, int tile_rows, int row0, uint32_t row_bytes = 128u) {
   return SwOp{tile + row0 * row_bytes, tile + tile_rows * row_bytes + row0 * 16u, tile_rows * 16u};

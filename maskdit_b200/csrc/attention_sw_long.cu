@@ -4,9 +4,10 @@
 // from the shared pre-kernel - with the tile fills done by bulk tensor copies (one 128-row box per block and tile part)
 // and the gradient tiles staged in smem and written by bulk tensor stores.
 //
-// STATUS: written at the end of round 1 after the GPU budget was spent; compiled, NOT yet run on hardware.  Dispatched
-// only with MDT_ATTN_SWL=1; first job of the next round: MDT_ATTN_SWL=1 pytest tests/test_kernels_gpu.py -k attention
-// (cases T = 512 / 1024).
+// STATUS: default path for T = 512 / 1024 (and the T = 256, head_dim 64/72 backward) since round 2: parity green on
+// B200 (tests/test_kernels_gpu.py::test_attention_fwd_bwd asserts this file's kernels ran), measured at B=128:
+// T=512,d_h=72 fwd 721 us / bwd 1601 us (attention_tc_long.cu: 860 / 1963); T=1024,d_h=32 fwd 1776 / bwd 3617 us
+// (2173 / 4311).  MDT_ATTN_SWL=0 switches back to attention_tc_long.cu for A/B runs.
 #include <stdlib.h>
 #include <string.h>
 
@@ -457,11 +458,11 @@ attn_swl_dkv_kernel(const __grid_constant__ CUtensorMap tq_a, const __grid_const
 // ------------------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------------------
-static bool attn_swl() {  // opt-in until the kernels have been run on hardware
+static bool attn_swl() {  // default since round 2 (B200: T=512 fwd 721 vs 860 us, bwd 1601 vs 1963 us); =0: A/B
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MDT_ATTN_SWL");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
 }

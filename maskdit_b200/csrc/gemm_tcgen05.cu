@@ -586,6 +586,7 @@ static int num_sms() {
   return g_num_sms;
 }
 
+extern int g_gemm_last_config;
 template <int BLOCK_N, bool A_MN, bool B_MN, int CG>
 static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, CG>;
@@ -644,9 +645,11 @@ static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
   attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr, cfg.numAttrs = 1;
   if (cudaLaunchKernelEx(&cfg, kern, ta, tb, p) != cudaSuccess) return MDT_ERR_CUDA;
+  g_gemm_last_config = BLOCK_N * 10 + CG;
   return cudaGetLastError() == cudaSuccess ? MDT_OK : MDT_ERR_CUDA;
 }
 
+int g_gemm_last_config = 0;  // BLOCK_N * 10 + CG of the last launch (tests assert the 2-CTA instances ran)
 static int g_force_cg = 0;  // 0 = auto, 1 / 2 = forced (MDT_GEMM_CG env, for A/B measurements)
 
 template <bool A_MN, bool B_MN>

@@ -159,6 +159,35 @@ __global__ void heun_kernel(int mode, const double* __restrict__ x_hat, const fl
   if (x_next_f32) x_next_f32[i] = static_cast<float>(xn);
 }
 
+// Generalised sampler state update (ablation_sampler, sample.py:73-188: every Euler / Heun / churn update is a linear
+// combination of the fp64 state, a second fp64 tensor and one fp32 network output with host-computed fp64 scalars):
+//   out = a*x + b*y + c*z ;  out_f32 = float(out * f32_scale)   (the next network input x / s(t))
+// Also: sample -> 8-bit pixel conversion of the sampler tail (sample.py:287): (v + 1) * 127.5 clamped, NCHW -> NHWC.
+__global__ void lincomb_f64_kernel(double a, const double* __restrict__ x, double b, const double* __restrict__ y,
+                                   double c, const float* __restrict__ z, double* __restrict__ out,
+                                   float* __restrict__ out_f32, double f32_scale, long long n) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  double v = a * x[i];
+  if (y) v += b * y[i];
+  if (z) v += c * static_cast<double>(z[i]);
+  if (out) out[i] = v;
+  if (out_f32) out_f32[i] = static_cast<float>(v * f32_scale);
+}
+
+__global__ void to_uint8_nhwc_kernel(const float* __restrict__ img, unsigned char* __restrict__ out, int B, int C,
+                                     int H, int W) {
+  const long long n = static_cast<long long>(B) * C * H * W;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;  // output index (b, h, w, c)
+  if (i >= n) return;
+  const int c = static_cast<int>(i % C);
+  const long long p = i / C;
+  const int w = static_cast<int>(p % W), h = static_cast<int>((p / W) % H), b = static_cast<int>(p / (static_cast<long long>(W) * H));
+  float v = (img[((static_cast<long long>(b) * C + c) * H + h) * W + w] + 1.f) * 127.5f;
+  v = fminf(fmaxf(v, 0.f), 255.f);
+  out[i] = static_cast<unsigned char>(v);  // truncation, as .to(torch.uint8)
+}
+
 // Fused AdamW + EMA + bf16 shadow, float4-vectorised over flat buffers.
 __global__ void __launch_bounds__(256)
 adamw_ema_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -193,6 +222,47 @@ adamw_ema_kernel(float* __restrict__ w, const float* __restrict__ g, float* __re
       reinterpret_cast<float4*>(ema)[i] = ev;
     }
     if (w16) reinterpret_cast<uint2*>(w16)[i] = make_uint2(pack_bf16(wv.x, wv.y), pack_bf16(wv.z, wv.w));
+  }
+}
+
+
+// Step front: VAE moments -> latent (utils.py:59-65), label dropout (train.py:209), sigma draw and
+// noise injection (train_utils/loss.py:35-39) in ONE pass over the batch, given the pre-drawn normals / uniforms
+// (drawn by the caller's generator in the reference's order).  Thread = 4 consecutive pixels of one channel plane.
+//   y  = sf * (mean + exp(0.5 clamp(logvar, -30, 20)) * eps)        sigma = exp(P_std * rnd + P_mean)
+//   yn = y + noise * sigma                                            labels[b, :] *= (drop_u[b] >= drop_prob)
+__global__ void __launch_bounds__(256)
+step_front_kernel(const float* __restrict__ moments, const float* __restrict__ eps, const float* __restrict__ rnd,
+                  const float* __restrict__ noise, const float* __restrict__ drop_u, float drop_prob, float sf,
+                  float P_mean, float P_std, float* __restrict__ y, float* __restrict__ yn, float* __restrict__ sigma,
+                  float* __restrict__ labels, int B, int C, int plane4, int nc) {
+  const long long per = static_cast<long long>(C) * plane4;  // float4 groups per sample
+  const long long total = static_cast<long long>(B) * per;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / per);
+    const long long r = i - b * per;  // (c, pixel group) inside the sample
+    const float sg = expf(rnd[b] * P_std + P_mean);
+    const float4* mom = reinterpret_cast<const float4*>(moments) + static_cast<long long>(b) * 2 * per;
+    const float4 mu = mom[r], lv = mom[per + r];
+    const float4 e = reinterpret_cast<const float4*>(eps)[i], nz = reinterpret_cast<const float4*>(noise)[i];
+    float4 o, on;
+    o.x = sf * (mu.x + expf(0.5f * fminf(fmaxf(lv.x, -30.f), 20.f)) * e.x);
+    o.y = sf * (mu.y + expf(0.5f * fminf(fmaxf(lv.y, -30.f), 20.f)) * e.y);
+    o.z = sf * (mu.z + expf(0.5f * fminf(fmaxf(lv.z, -30.f), 20.f)) * e.z);
+    o.w = sf * (mu.w + expf(0.5f * fminf(fmaxf(lv.w, -30.f), 20.f)) * e.w);
+    on = make_float4(fmaf(nz.x, sg, o.x), fmaf(nz.y, sg, o.y), fmaf(nz.z, sg, o.z), fmaf(nz.w, sg, o.w));
+    reinterpret_cast<float4*>(y)[i] = o;
+    reinterpret_cast<float4*>(yn)[i] = on;
+    if (r == 0) sigma[b] = sg;
+  }
+  if (labels && drop_u) {
+    const long long nl = static_cast<long long>(B) * nc;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nl;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const int b = static_cast<int>(i / nc);
+      if (!(drop_u[b] >= drop_prob)) labels[i] = 0.f;   // y * (rand >= p): dropped rows become the CFG-null label
+    }
   }
 }
 
@@ -259,6 +329,21 @@ int mdt_heun_update(int mode, const double* x_hat, const float* denoised, double
   return launch_status();
 }
 
+int mdt_lincomb_f64(double a, const double* x, double b, const double* y, double c, const float* z, double* out,
+                    float* out_f32, double f32_scale, long long n, void* stream) {
+  if (!x || (!out && !out_f32) || n <= 0) return MDT_ERR_ARG;
+  lincomb_f64_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, S(stream)>>>(a, x, b, y, c, z, out, out_f32,
+                                                                               f32_scale, n);
+  return launch_status();
+}
+
+int mdt_to_uint8_nhwc(const float* img, unsigned char* out, int B, int C, int H, int W, void* stream) {
+  if (!img || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return MDT_ERR_ARG;
+  const long long n = static_cast<long long>(B) * C * H * W;
+  to_uint8_nhwc_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, S(stream)>>>(img, out, B, C, H, W);
+  return launch_status();
+}
+
 int mdt_adamw_ema(float* w, const float* g, float* m, float* v, float* ema, void* w_bf16, long long n, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int step, float ema_decay,
                   float grad_scale, int max_blocks, void* stream) {
@@ -271,6 +356,24 @@ int mdt_adamw_ema(float* w, const float* g, float* m, float* v, float* ema, void
   adamw_ema_kernel<<<static_cast<int>(blocks), 256, 0, S(stream)>>>(
       w, g, m, v, ema, static_cast<__nv_bfloat16*>(w_bf16), n, lr, beta1, beta2, eps, weight_decay, inv_bc1, inv_bc2,
       ema_decay, grad_scale);
+  return launch_status();
+}
+
+int mdt_step_front(const float* moments, const float* eps, const float* rnd_normal, const float* noise_unit,
+                   const float* drop_u, float drop_prob, float scale_factor, float P_mean, float P_std, float* y,
+                   float* yn, float* sigma, float* labels, int B, int C, int R, int num_classes, void* stream) {
+  if (!moments || !eps || !rnd_normal || !noise_unit || !y || !yn || !sigma || B <= 0 || C <= 0 || R <= 0)
+    return MDT_ERR_ARG;
+  if ((R * R) % 4) return MDT_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(moments) | reinterpret_cast<uintptr_t>(eps) | reinterpret_cast<uintptr_t>(noise_unit) |
+       reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(yn)) & 15)
+    return MDT_ERR_ARG;
+  const long long total = static_cast<long long>(B) * C * (R * R / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  step_front_kernel<<<static_cast<int>(blocks), 256, 0, S(stream)>>>(moments, eps, rnd_normal, noise_unit, drop_u,
+                                                                     drop_prob, scale_factor, P_mean, P_std, y, yn,
+                                                                     sigma, labels, B, C, R * R / 4, num_classes);
   return launch_status();
 }
 

@@ -68,17 +68,52 @@ class EDMLoss:
     def __call__(self, net, images, labels=None, mask_ratio=0, mae_loss_coef=0, feat=None, augment_pipe=None):
         if feat is not None or augment_pipe is not None:
             raise NotImplementedError("feat / augment_pipe are not part of the MaskDiT latent training path")
+        raw = self._net(net, images.device)
+        B = images.shape[0]
+        y = images.contiguous().float()
+        rnd_normal = self._randn([B, 1, 1, 1], images.device)            # loss.py:35
+        sigma4 = (rnd_normal * self.P_std + self.P_mean).exp()            # loss.py:36
+        yn = (y + self._randn(tuple(y.shape), images.device) * sigma4).contiguous()  # loss.py:39,41
+        return self._finish(raw, y, yn, sigma4.reshape(B).contiguous(), labels, mask_ratio, mae_loss_coef)
+
+    def from_moments(self, net, moments, labels=None, mask_ratio=0, mae_loss_coef=0, class_dropout_prob=0.0,
+                     scale_factor=0.18215, eps=None, drop_u=None):
+        """The whole step front of the reference's training loop in one kernel (`ops.step_front`): `x = sample(x)`
+        (train.py:206, utils.py:59-65) -> label dropout (train.py:209) -> sigma draw + noise injection (loss.py:35-39),
+        then the same fused loss as `__call__`.  Random draws are made here in the reference's order: randn_like(mean),
+        rand[B,1] (only when class_dropout_prob > 0), randn[B,1,1,1], randn_like(images), then rand[B,L] for the mask.
+        `labels` is modified in place (dropped rows zeroed), as `y = y * (...)` rebinds it in the reference.
+        `eps` / `drop_u`: pre-drawn slices (gradient accumulation draws them once for the whole per-GPU batch before
+        the micro-batch rounds, train.py:206-209, so `TrainStep.step` passes them in)."""
+        dev = moments.device
+        raw = self._net(net, dev)
+        B, C2, R, _ = moments.shape
+        moments = moments.contiguous().float()
+        if eps is None:
+            eps = self._randn((B, C2 // 2, R, R), dev)
+        if class_dropout_prob > 0 and labels is not None:
+            if drop_u is None:
+                drop_u = self._rand((B, 1), dev).reshape(B)
+            drop_u = drop_u.contiguous()
+            if labels.dtype != torch.float32 or not labels.is_contiguous():
+                labels = labels.contiguous().float()
+        else:
+            drop_u = None
+        rnd_normal = self._randn([B, 1, 1, 1], dev).reshape(B).contiguous()
+        noise = self._randn((B, C2 // 2, R, R), dev)
+        y, yn, sigma = ops.step_front(moments, eps, rnd_normal, noise, labels, drop_u, float(class_dropout_prob),
+                                      scale_factor, self.P_mean, self.P_std)
+        return self._finish(raw, y, yn, sigma, labels, mask_ratio, mae_loss_coef)
+
+    def _net(self, net, dev):
         raw = _unwrap(net)
         if not isinstance(raw, EDMPrecond):
             raise TypeError("maskdit_b200.Losses['edm'] drives a maskdit_b200.EDMPrecond network")
-        dev = images.device
         raw._ready(dev)
-        B = images.shape[0]
-        y = images.contiguous().float()
-        rnd_normal = self._randn([B, 1, 1, 1], dev)                       # loss.py:35
-        sigma4 = (rnd_normal * self.P_std + self.P_mean).exp()            # loss.py:36
-        yn = (y + self._randn(tuple(y.shape), dev) * sigma4).contiguous()  # loss.py:39,41
-        sigma = sigma4.reshape(B).contiguous()
+        return raw
+
+    def _finish(self, raw, y, yn, sigma, labels, mask_ratio, mae_loss_coef):
+        dev, B = y.device, y.shape[0]
         _, _, lab = raw._norm_inputs(y, sigma, labels)
         md = None
         if mask_ratio > 0:

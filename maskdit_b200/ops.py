@@ -171,6 +171,23 @@ def edm_loss(F, xin, y, sigma, mask, gl, sigma_data, mae_coef, p, want_D=False, 
     return loss, Dx, dF
 
 
+def step_front(moments, eps, rnd_normal, noise_unit, labels=None, drop_u=None, drop_prob=0.0, scale_factor=0.18215,
+               P_mean=-1.2, P_std=1.2):
+    """moments -> latent, label dropout (in place on `labels`), sigma draw, noise injection: one launch.
+    Returns (y, yn, sigma)."""
+    _c(moments, f32), _c(eps, f32), _c(rnd_normal, f32), _c(noise_unit, f32), _c(labels, f32), _c(drop_u, f32)
+    B, C2, R, _ = moments.shape
+    C = C2 // 2
+    y = torch.empty(B, C, R, R, dtype=f32, device=moments.device)
+    yn = torch.empty_like(y)
+    sigma = torch.empty(B, dtype=f32, device=moments.device)
+    nc = labels.shape[1] if labels is not None else 0
+    check(lib().mdt_step_front(ptr(moments), ptr(eps), ptr(rnd_normal), ptr(noise_unit), ptr(drop_u), drop_prob,
+                               scale_factor, P_mean, P_std, ptr(y), ptr(yn), ptr(sigma),
+                               ptr(labels) if drop_u is not None else 0, B, C, R, nc, stream_ptr()), "mdt_step_front")
+    return y, yn, sigma
+
+
 def edm_precond_out(F, xin, sigma, sigma_data, p):
     B, C, R, _ = xin.shape
     Dx = torch.empty_like(xin)
@@ -199,6 +216,23 @@ def cfg_precond_out(F, xin, sigma, sigma_data, cfg_scale, p):
 def heun_update(mode, x_hat, denoised, d_cur, x_next, x_next_f32, t_hat, t_next):
     check(lib().mdt_heun_update(mode, ptr(x_hat), ptr(denoised), ptr(d_cur), ptr(x_next), ptr(x_next_f32),
                                 float(t_hat), float(t_next), x_hat.numel(), stream_ptr()), "mdt_heun_update")
+
+
+def lincomb_f64(a, x, b=0.0, y=None, c=0.0, z=None, out=None, out_f32=None, f32_scale=1.0):
+    """out = a*x + b*y + c*z (x, y fp64; z fp32), out_f32 = float(out * f32_scale).  Returns (out, out_f32)."""
+    _c(x, torch.float64), _c(y, torch.float64), _c(z, f32), _c(out, torch.float64), _c(out_f32, f32)
+    check(lib().mdt_lincomb_f64(float(a), ptr(x), float(b), ptr(y), float(c), ptr(z), ptr(out), ptr(out_f32),
+                                float(f32_scale), x.numel(), stream_ptr()), "mdt_lincomb_f64")
+    return out, out_f32
+
+
+def to_uint8_nhwc(img):
+    """[B,C,H,W] f32 in [-1,1] -> uint8 [B,H,W,C] (sample.py:287)."""
+    _c(img, f32)
+    B, C, H, W = img.shape
+    out = torch.empty(B, H, W, C, dtype=torch.uint8, device=img.device)
+    check(lib().mdt_to_uint8_nhwc(ptr(img), ptr(out), B, C, H, W, stream_ptr()), "mdt_to_uint8_nhwc")
+    return out
 
 
 def adamw_ema(w, g, m, v, ema, w16, n, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,

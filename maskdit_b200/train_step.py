@@ -57,7 +57,8 @@ def shard_batch(global_batch: int, world_size: int, rank: int):
 
 
 def lr_at(step: int, base_lr: float, global_batch: int, rampup_kimg: float):
-    """train.py:223 — note lr = 0 at step 0 when rampup_kimg > 0; with rampup 0 it is base_lr from step 1 on."""
+    """train.py:223, evaluated BEFORE `train_steps` is incremented (train.py:232): the very first update of a run
+    uses lr = 0 (also with lr_rampup_kimg = 0: min(0 / 1e-8, 1) = 0), every later one base_lr * min(ramp, 1)."""
     return base_lr * min(step * global_batch / max(rampup_kimg * 1000, 1e-8), 1)
 
 
@@ -72,13 +73,19 @@ def ar_chunk_bounds(n, k):
 class TrainStep:
     def __init__(self, net: EDMPrecond, ema: EDMPrecond | None = None, lr=1e-4, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=0.0, ema_decay=0.9999, loss_fn: EDMLoss | None = None, process_group=None,
-                 lr_rampup_kimg=0.0, global_batch=None, device=None, overlap=False, graph=None):
+                 lr_rampup_kimg=0.0, global_batch=None, device=None, overlap=False, graph=None,
+                 reference_lr_schedule=False):
         self.net, self.ema = net, ema
         self.lr, self.betas, self.eps, self.wd, self.ema_decay = lr, betas, eps, weight_decay, ema_decay
         self.loss_fn = loss_fn or EDMLoss()
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.rampup, self.global_batch = lr_rampup_kimg, global_batch
+        # lr: the reference recomputes it every step from the run's step counter (train.py:223); lr_step_offset lets a
+        # resumed run continue that counter when it differs from the optimizer's own step count.
+        self.reference_lr_schedule = reference_lr_schedule
+        self.lr_step_offset = 0
+        self._grad_scale = 1.0 / self.world
         self.step_count = 0
         dev = device or next(net.parameters()).device
         self.st = net.prepare(dev)
@@ -109,34 +116,60 @@ class TrainStep:
 
     # -- optimizer state for checkpoints (reference: train.py:259-270 stores optimizer.state_dict() under 'opt') ------
     def state_dict(self):
-        """Per-parameter AdamW state in named_parameters order, laid out like torch.optim.AdamW.state_dict()['state']
-        (exp_avg / exp_avg_sq / step), plus the hyper-parameters; tensors are copies on the current device."""
-        state, names = {}, []
-        for i, (k, p) in enumerate((k, p) for k, p in self.net.named_parameters() if p.requires_grad):
+        """AdamW state laid out like `torch.optim.AdamW(net.parameters()).state_dict()` / apex FusedAdam's
+        (train.py:141,262): `state` is keyed by the parameter's POSITION in `net.parameters()` — frozen tensors
+        (pos_embed = 0, decoder_pos_embed = 1) keep their index but own no state, so the first key is 2 — with
+        `exp_avg` / `exp_avg_sq` and a per-parameter `step` (torch layout); the step count is also stored in the
+        param_group (apex layout).  Tensors are copies on the current device."""
+        state, n_all = {}, 0
+        for i, (k, p) in enumerate(self.net.named_parameters()):
+            n_all = i + 1
+            if not p.requires_grad:
+                continue
             lo, _, shape = self.st.offsets[k]
             n = p.numel()
             state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.m[lo:lo + n].view(shape).clone(),
                         "exp_avg_sq": self.v[lo:lo + n].view(shape).clone()}
-            names.append(k)
-        return {"state": state, "param_names": names,
+        return {"state": state,
                 "param_groups": [{"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.wd,
-                                  "params": list(range(len(names)))}]}
+                                  "step": self.step_count, "params": list(range(n_all))}]}
 
     def load_state_dict(self, sd):
-        names = sd.get("param_names") or [k for k, p in self.net.named_parameters() if p.requires_grad]
-        if len(names) != len(sd["state"]):
-            raise ValueError(f"optimizer state holds {len(sd['state'])} tensors, the model has {len(names)}")
-        for i, k in enumerate(names):
-            e = sd["state"][i] if i in sd["state"] else sd["state"][str(i)]
+        """Accepts (a) this class's own layout, (b) `torch.optim.AdamW(model.parameters()).state_dict()`, (c) apex
+        FusedAdam's (same indexing, `step` only in the param_group) and (d) round-1 checkpoints of this repo (compact
+        indices over the trainable parameters + `param_names`)."""
+        state = {int(k): v for k, v in sd["state"].items()}
+        group = sd["param_groups"][0]
+        named = list(self.net.named_parameters())
+        trainable = [(i, k) for i, (k, p) in enumerate(named) if p.requires_grad]
+        if "param_names" in sd:                                    # (d) legacy compact layout
+            index_of = {k: j for j, k in enumerate(sd["param_names"])}
+            lookup = [(index_of[k], k) for _, k in trainable if k in index_of]
+        elif all(i in state for i, _ in trainable):                 # (a) (b) (c): position in net.parameters()
+            lookup = trainable
+        elif len(state) == len(trainable) and set(state) == set(range(len(trainable))):
+            lookup = [(j, k) for j, (_, k) in enumerate(trainable)]  # optimizer built over the trainable params only
+        else:
+            raise ValueError(f"optimizer state holds {len(state)} entries (keys {sorted(state)[:3]}..), the model has "
+                             f"{len(trainable)} trainable of {len(named)} parameters")
+        if len(lookup) != len(trainable):
+            raise ValueError(f"optimizer state covers {len(lookup)} of {len(trainable)} trainable parameters")
+        step = group.get("step", None)
+        for j, k in lookup:
+            e = state[j]
             lo, _, shape = self.st.offsets[k]
-            n = e["exp_avg"].numel()
             if tuple(e["exp_avg"].shape) != tuple(shape):
                 raise ValueError(f"optimizer state of {k}: shape {tuple(e['exp_avg'].shape)} != {tuple(shape)}")
+            n = e["exp_avg"].numel()
             self.m[lo:lo + n].copy_(e["exp_avg"].reshape(-1))
             self.v[lo:lo + n].copy_(e["exp_avg_sq"].reshape(-1))
-            self.step_count = int(float(e["step"]))
-        g = sd["param_groups"][0]
-        self.lr, self.betas, self.eps, self.wd = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
+            if "step" in e:
+                step = e["step"]
+        if step is None:
+            raise ValueError("optimizer state carries no step count (neither per parameter nor in the param_group)")
+        self.step_count = int(float(step))
+        self.lr, self.betas, self.eps, self.wd = group["lr"], tuple(group["betas"]), group["eps"], \
+            group["weight_decay"]
 
     # -- one gradient range: (all-reduce) + fused AdamW/EMA/bf16-shadow, on the current stream -----------------------
     def _reduce_and_step(self, lo, hi, max_blocks=0):
@@ -155,7 +188,7 @@ class TrainStep:
         ops.adamw_ema(st.w32[lo:hi], g, self.m[lo:hi], self.v[lo:hi],
                       self.ema_st.w32[lo:hi] if self.ema_st is not None else None, st.w16[lo:hi], n, self._lr_now,
                       self.step_count, self.betas[0], self.betas[1], self.eps, self.wd, self.ema_decay,
-                      1.0 / self.world, max_blocks)
+                      self._grad_scale, max_blocks)
 
     def _on_grads_ready(self, lo, hi):
         main = torch.cuda.current_stream()
@@ -166,19 +199,25 @@ class TrainStep:
             self._reduce_and_step(lo, hi, max_blocks=self.bg_blocks)
         self._done.append((lo, hi))
 
-    def _fwd_bwd_graphed(self, images, labels, mask_ratio, mae_loss_coef):
+    def _fwd_bwd_graphed(self, images, labels, mask_ratio, mae_loss_coef, loss_call, moments=False):
         """Gradient zeroing + loss forward + engine backward (~770 launches, 70 ms of host time) replayed from a CUDA
         graph captured once per (shapes, mask_ratio, mae_loss_coef); the all-reduce and the optimizer pass stay eager
         (their scalars change every step).  Opt-in (`TrainStep(graph=True)` / MDT_TRAIN_GRAPH=1): written at the end of
-        round 1 and NOT yet run on hardware."""
-        key = (tuple(images.shape), tuple(labels.shape), float(mask_ratio), float(mae_loss_coef))
+        round 1; run on B200 in round 2 (tests/test_model_gpu_extra.py::test_train_step_cuda_graph_matches_eager)."""
+        # keyed on the kept-token count (what shapes the launches), not on the float ratio: a schedule such as cos4
+        # (configs/finetune/imagenet256-latent-cos.yaml) revisits few distinct T; at most 2 graphs are kept.
+        L = self.net.model.num_patches
+        key = (tuple(images.shape), tuple(labels.shape), int(L * (1 - mask_ratio)) if mask_ratio > 0 else -1,
+               float(mae_loss_coef), bool(moments))
         ent = self._graphs.get(key)
         if ent is None:
+            while len(self._graphs) >= 2:
+                self._graphs.pop(next(iter(self._graphs)))
             gx, gy = images.clone(), labels.clone()
 
             def body():
                 self.st.grad.zero_()
-                loss = self.loss_fn(self.net, gx, gy, mask_ratio=mask_ratio, mae_loss_coef=mae_loss_coef)
+                loss = loss_call(self.net, gx, gy, mask_ratio, mae_loss_coef)
                 loss.mean().backward()
                 return loss.detach()
 
@@ -200,18 +239,59 @@ class TrainStep:
         ops.L.LAUNCHES += n_launch
         return out.clone()
 
-    def step(self, images, labels, mask_ratio=0.5, mae_loss_coef=0.1):
-        """One optimisation step on this rank's shard.  Returns the per-sample loss [B] (device tensor)."""
+    def step(self, images, labels, mask_ratio=0.5, mae_loss_coef=0.1, grad_accum=1, moments=False,
+             class_dropout_prob=0.0):
+        """One optimisation step on this rank's shard.  Returns the per-sample loss [B] (device tensor).
+        `grad_accum` > 1: the shard is cut into that many equal micro-batches whose mean-loss gradients are averaged
+        (train.py:211-227 under accelerate's `gradient_accumulation_steps`): the wgrad kernels accumulate into the
+        flat buffer anyway, so the rounds simply run back to back and 1/rounds is folded into the optimizer kernel.
+        `moments=True`: `images` are VAE moments [B,2C,R,R] straight from the dataset; the latent sampling, the label
+        dropout (`class_dropout_prob`) and the noise injection run as the fused step-front kernel (EDMLoss.from_moments)."""
         st = self.st
-        self.step_count += 1
+        if moments:
+            base_loss = self.loss_fn
+            pre = {}
+            if grad_accum > 1:   # the reference draws these once for the whole per-GPU batch (train.py:206-209)
+                Bt, C2, R, _ = images.shape
+                pre["eps"] = base_loss._randn((Bt, C2 // 2, R, R), images.device)
+                if class_dropout_prob > 0:
+                    pre["drop_u"] = base_loss._rand((Bt, 1), images.device).reshape(Bt)
+            rounds = [0]
+
+            def loss_call(net, x, lab, mask_ratio, mae_loss_coef):
+                n, r = x.shape[0], rounds[0]
+                rounds[0] += 1
+                sl = {k: v[r * n:(r + 1) * n].contiguous() for k, v in pre.items()}
+                return base_loss.from_moments(net, x, lab, mask_ratio=mask_ratio, mae_loss_coef=mae_loss_coef,
+                                              class_dropout_prob=class_dropout_prob, **sl)
+        else:
+            def loss_call(net, x, lab, mask_ratio, mae_loss_coef):
+                return self.loss_fn(net, x, lab, mask_ratio=mask_ratio, mae_loss_coef=mae_loss_coef)
         gb = self.global_batch or images.shape[0] * self.world
-        self._lr_now = lr_at(self.step_count, self.lr, gb, self.rampup) if self.rampup > 0 else self.lr
+        self._lr_now = lr_at(self.step_count + self.lr_step_offset, self.lr, gb, self.rampup) \
+            if self.reference_lr_schedule else self.lr
+        self.step_count += 1
         self._done = []
-        if self.graph and not self.overlap and ops.L.GEMM_PROFILE is None:
-            loss = self._fwd_bwd_graphed(images, labels, mask_ratio, mae_loss_coef)
+        self._grad_scale = 1.0 / (self.world * grad_accum)
+        if grad_accum > 1:
+            if images.shape[0] % grad_accum:
+                raise ValueError(f"batch {images.shape[0]} is not divisible by grad_accum {grad_accum}")
+            if self.overlap:
+                raise ValueError("overlap=True steps block ranges during the backward: incompatible with grad_accum > 1")
+            mb = images.shape[0] // grad_accum
+            st.grad.zero_()
+            losses = []
+            for r in range(grad_accum):
+                lr_ = loss_call(self.net, images[r * mb:(r + 1) * mb], labels[r * mb:(r + 1) * mb], mask_ratio,
+                                mae_loss_coef)
+                lr_.mean().backward()
+                losses.append(lr_.detach())
+            loss = torch.cat(losses)
+        elif self.graph and not self.overlap and ops.L.GEMM_PROFILE is None:
+            loss = self._fwd_bwd_graphed(images, labels, mask_ratio, mae_loss_coef, loss_call, moments)
         else:
             st.grad.zero_()
-            loss = self.loss_fn(self.net, images, labels, mask_ratio=mask_ratio, mae_loss_coef=mae_loss_coef)
+            loss = loss_call(self.net, images, labels, mask_ratio, mae_loss_coef)
             loss.mean().backward()   # engine backward; with overlap=True block ranges are already being reduced/stepped
         main = torch.cuda.current_stream()
         if self.overlap:

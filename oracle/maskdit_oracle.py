@@ -365,3 +365,101 @@ def adamw_ema_step(w, g, m, v, ema, step, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8, w
     w.addcdiv_(m / bc1, (v / bc2).sqrt() + eps, value=-lr)
     if ema is not None:
         ema.mul_(ema_decay).add_(w, alpha=1 - ema_decay)
+
+
+def step_front(moments, eps, rnd_normal, noise_unit, labels=None, drop_u=None, drop_prob=0.0, scale_factor=0.18215,
+               P_mean=-1.2, P_std=1.2):
+    """The step front of the reference's training loop given the pre-drawn randoms: utils.sample (utils.py:59-65),
+    label dropout (train.py:209), sigma draw + noise injection (train_utils/loss.py:35-39).
+    Returns (y, yn, sigma [B], labels)."""
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
+    y = scale_factor * (mean + std * eps)
+    if labels is not None and drop_u is not None and drop_prob > 0:
+        labels = labels * (drop_u.reshape(-1, 1) >= drop_prob)
+    sigma = (rnd_normal.reshape(-1, 1, 1, 1) * P_std + P_mean).exp()
+    return y, y + noise_unit * sigma, sigma.reshape(-1), labels
+
+
+def lr_schedule(train_steps, base_lr, global_batch, rampup_kimg):
+    """train.py:223, with `train_steps` the 0-based counter incremented after the update (train.py:232)."""
+    return base_lr * min(train_steps * global_batch / max(rampup_kimg * 1000, 1e-8), 1)
+
+
+def rank_batches(seeds, max_batch_size, rank, size):
+    """sample.py:232-235: seeds -> this rank's batches (tensor_split into a multiple of `size` parts, rank-strided)."""
+    num_batches = ((len(seeds) - 1) // (max_batch_size * size) + 1) * size
+    return [b.tolist() for b in torch.as_tensor(seeds).tensor_split(num_batches)[rank::size]]
+
+
+def ablation_sampler(denoise, latents, randn_like=torch.randn_like, num_steps=18, sigma_min=None, sigma_max=None,
+                     rho=7, solver="heun", discretization="edm", schedule="linear", scaling="none", epsilon_s=1e-3,
+                     C_1=0.001, C_2=0.008, M=1000, alpha=1, S_churn=0, S_min=0, S_max=float("inf"), S_noise=1,
+                     net_sigma_min=0.0, net_sigma_max=float("inf")):
+    """sample.py:73-188 restated with every schedule quantity a host-side fp64 scalar (the reference keeps them as
+    0-d fp64 tensors; `round_sigma` is the identity for EDMPrecond, models/maskdit.py:775).
+    `denoise(x_f32, sigma_float)` -> D.  Returns (x fp64, list of evaluated sigmas)."""
+    t64 = lambda v: torch.as_tensor(v, dtype=torch.float64)  # noqa: E731
+    vp_sigma = lambda bd, bm: (lambda t: float((np.e ** (0.5 * bd * (t ** 2) + bm * t) - 1) ** 0.5))  # noqa: E731
+    if sigma_min is None:
+        sigma_min = {"vp": vp_sigma(19.1, 0.1)(epsilon_s), "ve": 0.02, "iddpm": 0.002, "edm": 0.002}[discretization]
+    if sigma_max is None:
+        sigma_max = {"vp": vp_sigma(19.1, 0.1)(1), "ve": 100, "iddpm": 81, "edm": 80}[discretization]
+    sigma_min, sigma_max = max(sigma_min, net_sigma_min), min(sigma_max, net_sigma_max)
+    bd = 2 * (np.log(sigma_min ** 2 + 1) / epsilon_s - np.log(sigma_max ** 2 + 1)) / (epsilon_s - 1)   # sample.py:109
+    bm = np.log(sigma_max ** 2 + 1) - 0.5 * bd
+    idx = np.arange(num_steps, dtype=np.float64)
+    if discretization == "vp":
+        sig_steps = np.array([vp_sigma(bd, bm)(t) for t in 1 + idx / (num_steps - 1) * (epsilon_s - 1)])
+    elif discretization == "ve":
+        sig_steps = np.sqrt((sigma_max ** 2) * ((sigma_min ** 2 / sigma_max ** 2) ** (idx / (num_steps - 1))))
+    elif discretization == "iddpm":
+        # sample.py:118-121: `j` is an int64 tensor, so alpha_bar is evaluated in torch's default FLOAT32 (int tensor x
+        # python float) while u accumulates in fp64 - the type promotion is part of the reference's numbers.
+        ut = torch.zeros(M + 1, dtype=torch.float64)
+        abar = lambda j: (0.5 * np.pi * j / M / (C_2 + 1)).sin() ** 2  # noqa: E731
+        for j in torch.arange(M, 0, -1):
+            ut[j - 1] = ((ut[j] ** 2 + 1) / (abar(j - 1) / abar(j)).clip(min=C_1) - 1).sqrt()
+        u = ut.numpy()
+        uf = u[np.logical_and(u >= sigma_min, u <= sigma_max)]
+        sig_steps = uf[np.round((len(uf) - 1) / (num_steps - 1) * idx).astype(np.int64)]
+    else:
+        sig_steps = (sigma_max ** (1 / rho) + idx / (num_steps - 1) * (sigma_min ** (1 / rho) - sigma_max ** (1 / rho))) ** rho
+    if schedule == "vp":
+        sigma = vp_sigma(bd, bm)
+        sigma_deriv = lambda t: 0.5 * (bm + bd * t) * (sigma(t) + 1 / sigma(t))  # noqa: E731
+        sigma_inv = lambda s_: (np.sqrt(bm ** 2 + 2 * bd * np.log(s_ ** 2 + 1)) - bm) / bd  # noqa: E731
+    elif schedule == "ve":
+        sigma, sigma_deriv, sigma_inv = (lambda t: np.sqrt(t)), (lambda t: 0.5 / np.sqrt(t)), (lambda s_: s_ ** 2)
+    else:
+        sigma, sigma_deriv, sigma_inv = (lambda t: t), (lambda t: 1.0), (lambda s_: s_)
+    if scaling == "vp":
+        s = lambda t: 1 / np.sqrt(1 + sigma(t) ** 2)  # noqa: E731
+        s_deriv = lambda t: -sigma(t) * sigma_deriv(t) * (s(t) ** 3)  # noqa: E731
+    else:
+        s, s_deriv = (lambda t: 1.0), (lambda t: 0.0)
+    t_steps = [float(sigma_inv(v)) for v in sig_steps] + [0.0]
+    evals = []
+    x_next = latents.to(torch.float64) * (sigma(t_steps[0]) * s(t_steps[0]))
+    for i in range(num_steps):
+        t_cur, t_next = t_steps[i], t_steps[i + 1]
+        x_cur = x_next
+        gamma = min(S_churn / num_steps, np.sqrt(2) - 1) if S_min <= sigma(t_cur) <= S_max else 0
+        t_hat = float(sigma_inv(sigma(t_cur) + gamma * sigma(t_cur)))
+        x_hat = s(t_hat) / s(t_cur) * x_cur + float(np.sqrt(max(sigma(t_hat) ** 2 - sigma(t_cur) ** 2, 0))) * s(
+            t_hat) * S_noise * randn_like(x_cur)
+        h = t_next - t_hat
+        evals.append(float(sigma(t_hat)))
+        den = denoise((x_hat / s(t_hat)).float(), t64(sigma(t_hat))).to(torch.float64)
+        d_cur = (sigma_deriv(t_hat) / sigma(t_hat) + s_deriv(t_hat) / s(t_hat)) * x_hat - sigma_deriv(t_hat) * s(
+            t_hat) / sigma(t_hat) * den
+        x_prime, t_prime = x_hat + alpha * h * d_cur, t_hat + alpha * h
+        if solver == "euler" or i == num_steps - 1:
+            x_next = x_hat + h * d_cur
+        else:
+            evals.append(float(sigma(t_prime)))
+            den = denoise((x_prime / s(t_prime)).float(), t64(sigma(t_prime))).to(torch.float64)
+            d_prime = (sigma_deriv(t_prime) / sigma(t_prime) + s_deriv(t_prime) / s(t_prime)) * x_prime - \
+                sigma_deriv(t_prime) * s(t_prime) / sigma(t_prime) * den
+            x_next = x_hat + h * ((1 - 1 / (2 * alpha)) * d_cur + 1 / (2 * alpha) * d_prime)
+    return x_next, evals

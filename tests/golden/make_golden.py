@@ -115,7 +115,7 @@ def train_case(name, cfg, B, mask_ratio, with_grads):
     print(name, "loss", loss.detach().numpy())
 
 
-def eval_case(name, cfg, B):
+def eval_case(name, cfg, B, num_steps=18):
     net = build_ref(cfg).eval()
     images, labels = inputs(cfg, B, seed=11)
     sigma = torch.tensor([0.3, 2.5][:B] if B <= 2 else np.linspace(0.1, 5, B), dtype=torch.float32)
@@ -133,12 +133,12 @@ def eval_case(name, cfg, B):
             return orig_forward(x, sigma, *a, **k)
 
         net.forward = spy
-        z = rs.edm_sampler(net, latents, labels, cfg_scale=1.5, randn_like=rnd.randn_like, num_steps=18)
+        z = rs.edm_sampler(net, latents, labels, cfg_scale=1.5, randn_like=rnd.randn_like, num_steps=num_steps)
         net.forward = orig_forward
-    assert len(sig_seen) == 35
+    assert len(sig_seen) == 2 * num_steps - 1
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), images=images.numpy(), labels=labels.numpy(),
                         sigma=sigma.numpy(), D_plain=plain.numpy(), D_cfg=cfgout.numpy(), latents=latents.numpy(),
-                        z=z.numpy(), sampler_sigmas=np.array(sig_seen))
+                        z=z.numpy(), sampler_sigmas=np.array(sig_seen), num_steps=np.int64(num_steps))
     print(name, "sampler |z|", z.abs().mean().item())
 
 
@@ -193,7 +193,100 @@ def table_case():
     print("tables ok")
 
 
+def front_case(name):
+    """Step front of the training loop (train.py:206-209 + loss.py:35-39) executed with the reference's own functions:
+    utils.sample on VAE moments, label dropout, sigma draw, noise injection; all draws recorded."""
+    import utils as ru
+    B, C, R, ncls = 6, 4, 8, 10
+    g = torch.Generator().manual_seed(21)
+    moments = torch.randn(B, 2 * C, R, R, generator=g)
+    moments[0, C:] = 25.0      # logvar above the clamp (20)
+    moments[1, C:] = -40.0     # below the clamp (-30)
+    labels = torch.eye(ncls)[torch.randint(0, ncls, (B,), generator=g)]
+    drop_prob = 0.4
+    torch.manual_seed(77)
+    x = ru.sample(moments)                                                  # train.py:206
+    y = labels * (torch.rand([B, 1]) >= drop_prob)                         # train.py:209
+    rnd_normal = torch.randn([B, 1, 1, 1])                                 # loss.py:35
+    sigma = (rnd_normal * 1.2 - 1.2).exp()                                 # loss.py:36
+    n = torch.randn_like(x) * sigma                                        # loss.py:39
+    torch.manual_seed(77)                                                  # reproduce the draws
+    eps = torch.randn(B, C, R, R)
+    drop_u = torch.rand([B, 1])
+    rn2 = torch.randn([B, 1, 1, 1])
+    noise_unit = torch.randn(B, C, R, R)
+    assert torch.equal(rn2, rnd_normal)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), moments=moments.numpy(), labels=labels.numpy(),
+                        eps=eps.numpy(), drop_u=drop_u.reshape(B).numpy(), drop_prob=np.float32(drop_prob),
+                        rnd_normal=rnd_normal.reshape(B).numpy(), noise_unit=noise_unit.numpy(), y=x.numpy(),
+                        yn=(x + n).numpy(), sigma=sigma.reshape(B).numpy(), labels_out=y.numpy())
+    print(name, "dropped rows", int((y.sum(1) == 0).sum()))
+
+
+def ablation_case(name, cfg, B):
+    """ablation_sampler (sample.py:73-188) for every discretization / schedule / scaling family, both solvers, with
+    churn on one of them; 5 steps each."""
+    net = build_ref(cfg).eval()
+    _, labels = inputs(cfg, B, seed=17)
+    combos = [dict(solver="heun", discretization="edm", schedule="linear", scaling="none"),
+              dict(solver="euler", discretization="vp", schedule="vp", scaling="vp"),
+              dict(solver="heun", discretization="ve", schedule="ve", scaling="none"),
+              dict(solver="heun", discretization="iddpm", schedule="linear", scaling="none", alpha=0.75,
+                   S_churn=10.0, S_min=0.05, S_max=50.0, S_noise=1.003),
+              dict(solver="heun", discretization="vp", schedule="linear", scaling="vp")]
+    out = dict(labels=labels.numpy(), n=np.int64(len(combos)))
+    with torch.no_grad():
+        for ci, kw in enumerate(combos):
+            rnd = rs.StackedRandomGenerator("cpu", list(range(B)))
+            latents = rnd.randn([B, cfg.img_channels, cfg.img_resolution, cfg.img_resolution])
+            noises, sig_seen = [], []
+
+            def randn_like(x):
+                nz = rnd.randn_like(x)
+                noises.append(nz.numpy().copy())
+                return nz
+
+            orig_forward = net.forward
+
+            def spy(x, sigma, *a, **k):
+                sig_seen.append(float(sigma))
+                return orig_forward(x, sigma, *a, **k)
+
+            net.forward = spy
+            z = rs.ablation_sampler(net, latents, labels, cfg_scale=1.5 if ci % 2 == 0 else None,
+                                    randn_like=randn_like, num_steps=5, **kw)
+            net.forward = orig_forward
+            out[f"latents{ci}"], out[f"z{ci}"] = latents.numpy(), z.numpy()
+            out[f"noises{ci}"], out[f"sigmas{ci}"] = np.stack(noises), np.array(sig_seen)
+            out[f"kw{ci}"] = np.array(repr(kw))
+            print(name, ci, kw["discretization"], "evals", len(sig_seen), "|z|", z.abs().mean().item())
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+
+
+def round2_cases():
+    """Round 2: goldens that reach the PRODUCTION kernels: XL/2 at R=32 has T=128 kept tokens,
+    so B=2 gives M=256 token rows (2-CTA GEMM tiles) and the split-tile tcgen05 attention forward/backward
+    (head_dim 72 / 32); the eval/CFG case runs T=256, head_dim 72; R=64 runs the blocked T=512 / L=1024 kernels."""
+    xl = O.Cfg(model_type="DiT-XL/2", img_resolution=32, num_classes=1000)
+    train_case("xl2_c1_grads", xl, B=2, mask_ratio=0.5, with_grads=True)
+    eval_case("xl2_eval", xl, B=2, num_steps=3)
+    xl64 = O.Cfg(model_type="DiT-XL/2", img_resolution=64, num_classes=1000)
+    train_case("xl2_r64_grads", xl64, B=1, mask_ratio=0.5, with_grads=True)
+    round2_small()
+
+
+def round2_small():
+    front_case("step_front")
+    ablation_case("s2_ablation", O.Cfg(model_type="DiT-S/2", img_resolution=8, num_classes=10), B=2)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        round2_cases()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "round2_small":
+        round2_small()
+        sys.exit(0)
     small = O.Cfg(model_type="DiT-S/2", img_resolution=8, num_classes=10)
     train_case("s2_train_mask", small, B=2, mask_ratio=0.5, with_grads=True)
     train_case("s2_train_nomask", small, B=2, mask_ratio=0.0, with_grads=True)
@@ -205,3 +298,4 @@ if __name__ == "__main__":
     train_case("b4_train_mask75", b4, B=3, mask_ratio=0.75, with_grads=True)
     xl = O.Cfg(model_type="DiT-XL/2", img_resolution=32, num_classes=1000)
     train_case("xl2_c1_fwd", xl, B=2, mask_ratio=0.5, with_grads=False)
+    round2_cases()

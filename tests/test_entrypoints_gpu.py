@@ -47,9 +47,39 @@ def test_train_then_generate(tmp_path):
     assert "Train Loss" in out
     ck = tmp_path / "res" / "checkpoints" / "0000004.pt"
     assert ck.exists()
-    sd = torch.load(ck, map_location="cpu")
+    sd = torch.load(ck, map_location="cpu", weights_only=False)
     assert set(sd) >= {"model", "ema"} and "model.blocks.0.attn.qkv.weight" in sd["ema"]
     out = run([os.path.join(ROOT, "generate.py"), "--config", str(cfg), "--ckpt_path", str(ck), "--seeds", "0-3",
                "--num_steps", "6", "--cfg_scale", "1.5", "--results_dir", str(tmp_path / "samples")], str(tmp_path))
     z = np.load(tmp_path / "samples" / "000002.npy")
     assert z.shape == (4, 16, 16) and np.isfinite(z).all()
+
+
+def test_train_from_lmdb_dataset_with_grad_accum_then_resume_and_ablation_generate(tmp_path):
+    """train.py WITHOUT --synthetic: the reference's LMDB latent layout (z-{i} / y-{i} / length) feeds the fused step
+    front; grad_accum = 2; the checkpoint stores `args` as a Namespace like the reference's and resumes; generate.py
+    runs the ablation sampler rank-strided (single rank here)."""
+    sys.path.insert(0, ROOT)
+    from maskdit_b200.data import write_latent_lmdb
+    rng = np.random.default_rng(0)
+    write_latent_lmdb(str(tmp_path / "data"), rng.standard_normal((64, 8, 16, 16)).astype(np.float32),
+                      rng.integers(0, 1000, 64))
+    cfg = tmp_path / "cfg.yaml"
+    cfg.write_text(YAML.replace("root: none", f"root: {tmp_path / 'data'}").replace("batchsize: 8, grad_accum: 1",
+                                                                                  "batchsize: 4, grad_accum: 2"))
+    out = run([os.path.join(ROOT, "train.py"), "--config", str(cfg), "--max_steps", "4", "--results_dir",
+               str(tmp_path / "res")], str(tmp_path))
+    assert "Dataset contains 64 images" in out and "Train Loss" in out
+    ck = tmp_path / "res" / "checkpoints" / "0000004.pt"
+    sd = torch.load(ck, map_location="cpu", weights_only=False)
+    import argparse
+    assert isinstance(sd["args"], argparse.Namespace) and min(sd["opt"]["state"]) == 2
+    out = run([os.path.join(ROOT, "train.py"), "--config", str(cfg), "--max_steps", "2", "--results_dir",
+               str(tmp_path / "res")], str(tmp_path))            # resumes from 0000004.pt
+    assert "(step=0000006)" in out
+    run([os.path.join(ROOT, "generate.py"), "--config", str(cfg), "--ckpt_path", str(ck), "--seeds", "0-2",
+         "--num_steps", "4", "--solver", "euler", "--discretization", "vp", "--schedule", "vp", "--scaling", "vp",
+         "--png_preview", "--results_dir", str(tmp_path / "samples")], str(tmp_path))
+    z = np.load(tmp_path / "samples" / "000001.npy")
+    assert z.shape == (4, 16, 16) and np.isfinite(z).all()
+    assert open(tmp_path / "samples" / "000001.png", "rb").read(8) == b"\x89PNG\r\n\x1a\n"

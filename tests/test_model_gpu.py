@@ -3,8 +3,8 @@ unmodified reference and (b) the CPU oracle on the same seeded inputs.
 
 Tolerance: GEMM operands are bf16 (fp32 accumulate; fp32 residual stream / LN / softmax / loss),
 so elementwise rtol 1e-3 against an fp32 run is not attainable by ANY bf16 implementation — PyTorch's own bf16
-autocast of the reference measures rel-L2 2.2e-3.  We assert rel-L2 <= 1e-2 on outputs, 3e-2 on gradients
-(bf16 backward), loss within 1e-2 relative; the integer mask path is bit-exact."""
+autocast of the reference measures rel-L2 2.2e-3.  We assert rel-L2 <= 3e-3 on outputs (measured 2.0e-3), 1.5e-2 on
+gradients (bf16 backward; measured 0.7-0.8e-2), loss within 5e-3 relative; the integer mask path is bit-exact."""
 import copy
 import os
 import sys
@@ -39,6 +39,66 @@ def build(model_type="DiT-S/2", R=8, ncls=10, seed=1):
     return net.cuda(), cfg, sd
 
 
+FWD_TOL, GRAD_TOL, LOSS_TOL = 3e-3, 1.5e-2, 5e-3   # rel-L2 outputs / rel-L2 gradients / relative loss
+
+
+def check_grads(net, g, tol=GRAD_TOL, what=""):
+    """Every parameter-gradient norm, the stored full gradients and the stored 4x8 slices against the reference's."""
+    worst, n = (0.0, ""), 0
+    for k, p in net.named_parameters():
+        key = f"gnorm/{k}"
+        if key not in g:
+            continue
+        gn, ref = p.grad.double().norm().item(), float(g[key])
+        assert abs(gn - ref) <= tol * ref + 1e-7, (k, gn, ref)
+        n += 1
+        if f"grad/{k}" in g and ref > 0:
+            r = rel_l2(p.grad, g[f"grad/{k}"])
+            worst = max(worst, (r, k))
+            assert r <= tol, (k, r)
+        if f"gslice/{k}" in g and ref > 0:
+            sl = p.grad.reshape(p.grad.shape[0], -1)[:4, :8]
+            want = g[f"gslice/{k}"]
+            # a 32-element slice: compare against the scale of the whole tensor (rms), bf16 backward noise
+            rms = ref / max(p.grad.numel(), 1) ** 0.5
+            assert (sl.cpu().double() - want.double()).abs().max().item() <= 8 * tol * rms + 1e-9, k
+    assert n > 100
+    print(what, "worst grad rel-L2", worst, "over", n, "tensors")
+
+
+class ImplRecorder:
+    """Records which GEMM instance (BLOCK_N*10 + CTAs per tile) and which attention kernel family served every call
+    made by the engine inside the `with` block (mdt_gemm_last_config / mdt_attention_last_impl)."""
+
+    def __enter__(self):
+        from maskdit_b200 import engine, ops
+        self.engine, self.ops = engine, ops
+        self.gemm_cfgs, self.attn_fwd, self.attn_bwd = set(), set(), set()
+        self._g, self._f, self._b = engine.gemm, ops.attention_fwd, ops.attention_bwd
+        L = ops.lib()
+
+        def gemm(*a, **k):
+            r = self._g(*a, **k)
+            self.gemm_cfgs.add(L.mdt_gemm_last_config())
+            return r
+
+        def afwd(qkv, B, T, H, dh, **k):
+            r = self._f(qkv, B, T, H, dh, **k)
+            self.attn_fwd.add((T, dh, L.mdt_attention_last_impl(0)))
+            return r
+
+        def abwd(qkv, out, dout, lse, B, T, H, dh):
+            r = self._b(qkv, out, dout, lse, B, T, H, dh)
+            self.attn_bwd.add((T, dh, L.mdt_attention_last_impl(1)))
+            return r
+
+        engine.gemm, ops.attention_fwd, ops.attention_bwd = gemm, afwd, abwd
+        return self
+
+    def __exit__(self, *exc):
+        self.engine.gemm, self.ops.attention_fwd, self.ops.attention_bwd = self._g, self._f, self._b
+
+
 class GoldenLoss:
     """EDMLoss with the golden random draws injected in the reference's draw order."""
 
@@ -51,13 +111,16 @@ class GoldenLoss:
                 self.q_randn = [g["rnd_normal"].cuda(), g["noise_unit"].cuda()]
                 self.q_rand = [g["mask_noise"].cuda()] if "mask_noise" in g else []
 
-            def _randn(self, shape, device):
-                t = self.q_randn.pop(0)
+                self.n_randn = 0
+
+            def _randn(self, shape, device):   # draws cycle (sigma, noise, sigma, noise, ...): reusable across steps
+                t = self.q_randn[self.n_randn % 2]
+                self.n_randn += 1
                 assert tuple(t.shape) == tuple(shape)
                 return t
 
             def _rand(self, shape, device):
-                return self.q_rand.pop(0)
+                return self.q_rand[0]
 
         return _L()
 
@@ -73,21 +136,9 @@ def test_train_loss_and_grads_vs_reference_golden(name):
     if mr > 0:  # integer path: bit-exact
         for k in ("mask", "ids_keep", "ids_restore"):
             assert torch.equal(lf.last_mask_dict[k].cpu(), g[k]), k
-    assert torch.allclose(loss.cpu(), g["loss"], rtol=1e-2), (loss, g["loss"])
+    assert torch.allclose(loss.cpu(), g["loss"], rtol=LOSS_TOL), (loss, g["loss"])
     loss.mean().backward()
-    worst = 0.0
-    for k, p in net.named_parameters():
-        key = f"gnorm/{k}"
-        if key not in g:
-            continue
-        gn = p.grad.double().norm().item()
-        ref = float(g[key])
-        assert abs(gn - ref) <= 3e-2 * ref + 1e-7, (k, gn, ref)
-        if f"grad/{k}" in g:
-            r = rel_l2(p.grad, g[f"grad/{k}"]) if ref > 0 else 0.0
-            worst = max(worst, r)
-            assert r <= 3e-2, (k, r)
-    print("worst grad rel-L2", worst)
+    check_grads(net, g)
 
 
 def test_generic_autograd_path_matches_fused():
@@ -157,9 +208,9 @@ def test_eval_cfg_and_sampler_vs_reference_golden():
     net.eval()
     with torch.no_grad():
         plain = net(g["images"].cuda(), g["sigma"].cuda(), g["labels"].cuda())["x"]
-        assert rel_l2(plain, g["D_plain"]) <= 1e-2
+        assert rel_l2(plain, g["D_plain"]) <= FWD_TOL
         c = net(g["images"].cuda(), torch.tensor(1.7, dtype=torch.float64).cuda(), g["labels"].cuda(), 1.5)["x"]
-        assert rel_l2(c, g["D_cfg"]) <= 1e-2
+        assert rel_l2(c, g["D_cfg"]) <= FWD_TOL
         calls = []
         orig = net.forward
 
@@ -192,8 +243,8 @@ def test_xl2_config1_forward_vs_reference_golden():
         assert torch.equal(lf.last_mask_dict[k].cpu(), g[k])
     r = rel_l2(D, g["D"])
     print("XL/2 C1 forward rel-L2 vs reference fp32:", r, "loss", loss.cpu(), g["loss"])
-    assert r <= 1e-2
-    assert torch.allclose(loss.cpu(), g["loss"], rtol=1e-2)
+    assert r <= FWD_TOL
+    assert torch.allclose(loss.cpu(), g["loss"], rtol=LOSS_TOL)
 
 
 @pytest.mark.parametrize("overlap", [False, True])
@@ -217,7 +268,7 @@ def test_train_step_matches_oracle_adamw_and_ema(overlap):
         ts.loss_fn = GoldenLoss(g)
         loss = ts.step(g["images"].cuda(), g["labels"].cuda(), 0.5, 0.1)
         lo, _ = O.edm_loss(sdr, cfg, g["images"], g["labels"], g["rnd_normal"], g["noise_unit"], md, 0.1)
-        assert torch.allclose(loss.cpu(), lo.detach(), rtol=2e-2), (step, loss, lo)
+        assert torch.allclose(loss.cpu(), lo.detach(), rtol=1e-2), (step, loss, lo)
         for v in sdr.values():
             v.grad = None
         lo.mean().backward()
@@ -231,11 +282,12 @@ def test_train_step_matches_oracle_adamw_and_ema(overlap):
         d_gpu = (new[k].cpu() - sd[k]).flatten()
         d_ref = (sdr[k].detach() - sd[k]).flatten()
         cos = torch.nn.functional.cosine_similarity(d_gpu, d_ref, dim=0).item()
-        assert cos > 0.9, (k, cos)
+        print("weight-delta cosine", k, cos)
+        assert cos > 0.95, (k, cos)
     k = "model.blocks.0.mlp.fc1.weight"
     e_gpu = ema.state_dict()[k].cpu() - sd[k]
     e_ref = er[k] - sd[k]
-    assert torch.nn.functional.cosine_similarity(e_gpu.flatten(), e_ref.flatten(), dim=0).item() > 0.9
+    assert torch.nn.functional.cosine_similarity(e_gpu.flatten(), e_ref.flatten(), dim=0).item() > 0.95
 
 
 def test_train_step_state_dict_resume():

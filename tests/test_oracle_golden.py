@@ -37,7 +37,12 @@ def test_tables_match_reference():
 B4 = O.Cfg(model_type="DiT-B/4", img_resolution=16, num_classes=7)  # patch 4, 12 heads of 64, 16 patches
 
 
-@pytest.mark.parametrize("name,CFG", [("s2_train_mask", SMALL), ("s2_train_nomask", SMALL), ("b4_train_mask75", B4)])
+XL32 = O.Cfg(model_type="DiT-XL/2", img_resolution=32, num_classes=1000)
+XL64 = O.Cfg(model_type="DiT-XL/2", img_resolution=64, num_classes=1000)
+
+
+@pytest.mark.parametrize("name,CFG", [("s2_train_mask", SMALL), ("s2_train_nomask", SMALL), ("b4_train_mask75", B4),
+                                      ("xl2_c1_grads", XL32), ("xl2_r64_grads", XL64)])
 def test_train_loss_and_grads_match_reference(name, CFG):
     g = load(name)
     SMALL = CFG  # noqa: N806 - the body below is written against the small config's name
@@ -116,3 +121,61 @@ def test_xl2_config1_forward_matches_reference():
                              cfg.mae_loss_coef)
     np.testing.assert_allclose(loss.numpy(), g["loss"], rtol=1e-4)
     np.testing.assert_allclose(D.numpy(), g["D"], rtol=1e-3, atol=1e-4)
+
+
+def test_xl2_eval_cfg_and_short_sampler_match_reference():
+    """XL/2 unmasked eval + CFG forward (BASELINE config 5's network evaluation: 256 tokens, 16 heads of 72) and a
+    3-step (5-evaluation) CFG sampler run."""
+    g = load("xl2_eval")
+    sd = O.make_state_dict(XL32, 1)
+    lab = t(g["labels"])
+    with torch.no_grad():
+        plain = O.edm_precond(sd, XL32, t(g["images"]), t(g["sigma"]), lab, training=False)
+        np.testing.assert_allclose(plain.numpy(), g["D_plain"], rtol=1e-3, atol=1e-4)
+        cfg = O.edm_precond(sd, XL32, t(g["images"]), torch.tensor(1.7, dtype=torch.float64), lab, cfg_scale=1.5,
+                            training=False)
+        np.testing.assert_allclose(cfg.numpy(), g["D_cfg"], rtol=1e-3, atol=1e-4)
+        z, evals = O.edm_sampler(lambda x, s: O.edm_precond(sd, XL32, x, s, lab, cfg_scale=1.5, training=False),
+                                 t(g["latents"]), num_steps=int(g["num_steps"]))
+    np.testing.assert_allclose(np.array(evals), g["sampler_sigmas"], rtol=1e-12)
+    np.testing.assert_allclose(z.numpy(), g["z"], rtol=1e-3, atol=1e-3)
+
+
+def test_step_front_matches_reference():
+    """utils.sample + label dropout + sigma draw + noise injection (train.py:206-209, loss.py:35-39)."""
+    g = load("step_front")
+    y, yn, sigma, lab = O.step_front(t(g["moments"]), t(g["eps"]), t(g["rnd_normal"]), t(g["noise_unit"]),
+                                     t(g["labels"]), t(g["drop_u"]), float(g["drop_prob"]))
+    assert np.array_equal(y.numpy(), g["y"]) and np.array_equal(lab.numpy(), g["labels_out"])
+    np.testing.assert_allclose(sigma.numpy(), g["sigma"], rtol=1e-6)
+    np.testing.assert_allclose(yn.numpy(), g["yn"], rtol=1e-6, atol=1e-6)
+    assert 0 < int((lab.sum(1) == 0).sum()) < lab.shape[0]
+
+
+def test_ablation_sampler_matches_reference():
+    """sample.py:73-188: every discretization / schedule / scaling family, Euler and Heun, churn, alpha != 1."""
+    g = load("s2_ablation")
+    sd = O.make_state_dict(SMALL, 1)
+    lab = t(g["labels"])
+    for ci in range(int(g["n"])):
+        kw = eval(str(g[f"kw{ci}"]))  # noqa: S307 - our own fixture
+        noises = [t(n) for n in g[f"noises{ci}"]]
+        cs = 1.5 if ci % 2 == 0 else None
+        with torch.no_grad():
+            z, evals = O.ablation_sampler(
+                lambda x, s: O.edm_precond(sd, SMALL, x, s, lab, cfg_scale=cs, training=False), t(g[f"latents{ci}"]),
+                randn_like=lambda x: noises.pop(0), num_steps=5, **kw)
+        assert not noises
+        np.testing.assert_allclose(np.array(evals), g[f"sigmas{ci}"], rtol=1e-9, err_msg=str(kw))
+        scale = np.abs(g[f"z{ci}"]).max()
+        np.testing.assert_allclose(z.numpy(), g[f"z{ci}"], rtol=2e-3, atol=2e-4 * scale, err_msg=str(kw))
+
+
+def test_lr_schedule_and_rank_batches():
+    assert O.lr_schedule(0, 1e-4, 1024, 0) == 0.0 and O.lr_schedule(1, 1e-4, 1024, 0) == 1e-4   # train.py:223
+    assert abs(O.lr_schedule(5, 1e-4, 1024, 10) - 1e-4 * 5 * 1024 / 10000) < 1e-18
+    seeds = list(range(100, 170))
+    got = [O.rank_batches(seeds, 8, r, 4) for r in range(4)]
+    assert sorted(s for rb in got for b in rb for s in b) == seeds
+    assert all(len(b) <= 8 for rb in got for b in rb) and len({len(rb) for rb in got}) == 1
+    assert got[1][0] == list(range(100 + 6, 100 + 12))   # 70 seeds -> 12 batches of 6/5, rank 1 takes batch 1, 5, 9

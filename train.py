@@ -8,8 +8,11 @@ Differences from the reference driver, all outside the arithmetic: PyYAML instea
 `accelerate launch`; bf16 GEMM operands instead of fp16 AMP + GradScaler (`--no_amp` is accepted and ignored: there
 is one precision recipe); the DDP wrapper + apex FusedAdam + EMA loop are replaced by `TrainStep` (single flat
 all-reduce, fused AdamW+EMA); wandb / FID-during-training are not wired (out of scope).
-Data: `--synthetic` draws latents of the configured shape (no dataset on this box); LMDB latents
-(train_utils/datasets.py:240-304) are read when the `lmdb` module is importable.
+Data: the reference's LMDB latent dataset (`data.root`/train: keys z-{i} / y-{i} / length, train_utils/datasets.py:
+240-304) through `maskdit_b200.data` (liblmdb when the `lmdb` module exists, otherwise a read-only page walker of
+data.mdb); `--synthetic` draws VAE moments of the configured shape instead (no dataset on the bench boxes).  Either
+way the moments -> latent sampling, label dropout and noise injection run as ONE fused kernel (`ops.step_front`),
+gradient accumulation (`train.grad_accum`) and the lr ramp follow train.py:211-227.
 """
 import argparse
 import copy
@@ -41,13 +44,6 @@ def synthetic_loader(cfg, batch, device, seed):
         yield moments, labels
 
 
-def sample_latent(moments, scale_factor=0.18215):
-    """utils.sample (utils.py:59-65): VAE moments -> latent."""
-    mean, logvar = torch.chunk(moments, 2, dim=1)
-    std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
-    return scale_factor * (mean + std * torch.randn_like(mean))
-
-
 def main():
     ap = argparse.ArgumentParser("training parameters")
     ap.add_argument("--config", required=True)
@@ -77,59 +73,74 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     torch.manual_seed(args.global_seed)  # same seed on every rank, as the reference (train.py:67-68)
 
-    batch = cfg.train.batchsize
-    global_batch = batch * cfg.train.grad_accum * world
+    micro_batch = cfg.train.batchsize                      # train.py:72-75
+    rounds = int(cfg.train.get("grad_accum", 1) or 1)
+    batch = micro_batch * rounds                           # per-GPU batch of one optimizer step
+    global_batch = batch * world
     net = build_net(cfg).to(device).train()
     ema = copy.deepcopy(net).eval()
     for p in ema.parameters():
         p.requires_grad_(False)
     step0 = 0
     ck = args.ckpt_path or latest_ckpt(os.path.join(args.results_dir, "checkpoints"))
+    ts = None
+    strict = str(args.use_strict_load).lower() in ("true", "1")
     if ck:
-        sd = torch.load(ck, map_location=device)
-        strict = str(args.use_strict_load).lower() in ("true", "1")
+        # reference checkpoints store `args` as an argparse.Namespace (train.py:259-265): a full (trusted) unpickle
+        sd = torch.load(ck, map_location=device, weights_only=False)
         net.load_state_dict({k.replace("_orig_mod.", ""): v for k, v in sd["model"].items()}, strict=strict)
         ema.load_state_dict({k.replace("_orig_mod.", ""): v for k, v in sd["ema"].items()}, strict=strict)
         step0 = int(os.path.basename(ck)[:-3]) if os.path.basename(ck)[:-3].isdigit() else 0
     ts = TrainStep(net, ema, lr=cfg.train.lr, lr_rampup_kimg=cfg.train.lr_rampup_kimg, global_batch=global_batch,
-                   loss_fn=Losses[cfg.model.precond]())
-    if ck and "opt" in sd and "state" in sd["opt"]:
+                   loss_fn=Losses[cfg.model.precond](), reference_lr_schedule=True)
+    if ck and strict and "opt" in sd:                      # train.py:150: optimizer state only under strict loading
         ts.load_state_dict(sd["opt"])
+    ts.lr_step_offset = step0 - ts.step_count              # lr follows the run's step counter (train.py:223)
     ratio_fn = mask_ratio_schedule(cfg.model.get("mask_ratio_fn", "constant"), cfg.model.mask_ratio,
                                    cfg.model.get("mask_ratio_min", 0) or 0)
     drop = cfg.model.get("class_dropout_prob", 0) or 0
     max_steps = args.max_steps or cfg.train.get("max_num_steps", 10 ** 9)
-    if not args.synthetic:
-        raise SystemExit("LMDB latent loading needs the `lmdb` module and the dataset at data.root; "
-                         "run with --synthetic on this box")
-    loader = synthetic_loader(cfg, batch, device, args.global_seed + rank)
+    if args.synthetic:
+        loader = synthetic_loader(cfg, batch, device, args.global_seed + rank)
+    else:
+        from maskdit_b200.data import ImageNetLatentDataset, batches
+        ds = ImageNetLatentDataset(cfg.data.root, resolution=cfg.data.resolution, num_channels=cfg.data.num_channels,
+                                   num_classes=cfg.model.num_classes)
+        if rank == 0:
+            print(f"Dataset contains {len(ds):,} images ({cfg.data.root})", flush=True)
+        loader = batches(ds, batch, rank, world, start=step0)
     log_every = cfg.log.log_every
-    running, t0, step = 0.0, time.time(), step0
+    running, log_steps, t0, step = 0.0, 0, time.time(), step0
     for moments, labels in loader:
-        x = sample_latent(moments)
-        if drop > 0:
-            labels = labels * (torch.rand(labels.shape[0], 1, device=device) >= drop)   # train.py:209
+        moments = moments.to(device, non_blocking=True)
+        labels = labels.to(device, non_blocking=True)
         ratio = ratio_fn((step - step0) / max_steps)
-        loss = ts.step(x, labels, ratio, cfg.model.mae_loss_coef)
+        # moments -> latent (train.py:206), label dropout (:209), noise injection (loss.py:35-39): fused step front
+        loss = ts.step(moments, labels, ratio, cfg.model.mae_loss_coef, grad_accum=rounds, moments=True,
+                       class_dropout_prob=drop)
         running = running + loss.mean()
+        log_steps += 1
         step += 1
-        if step % log_every == 0 or step - step0 == max_steps:
-            avg = running / log_every
+        if step - step0 > max_steps:
+            break
+        if step % log_every == 0:
+            avg = running / log_steps
             if world > 1:
                 dist.all_reduce(avg)
                 avg = avg / world
             torch.cuda.synchronize()
             if rank == 0:
                 print(f"(step={step:07d}) Train Loss: {float(avg):.4f}, Train Steps/Sec: "
-                      f"{log_every / (time.time() - t0):.2f}", flush=True)
-            running, t0 = 0.0, time.time()
-        if step % cfg.log.ckpt_every == 0 and rank == 0:
-            d = os.path.join(args.results_dir, "checkpoints")
-            os.makedirs(d, exist_ok=True)
-            torch.save({"model": net.state_dict(), "ema": ema.state_dict(), "opt": ts.state_dict(), "args": vars(args)},
-                       os.path.join(d, f"{step:07d}.pt"))
-        if step - step0 >= max_steps:
-            break
+                      f"{log_steps / (time.time() - t0):.2f}", flush=True)
+            running, log_steps, t0 = 0.0, 0, time.time()
+        if step % cfg.log.ckpt_every == 0 and step > step0:
+            if rank == 0:
+                d = os.path.join(args.results_dir, "checkpoints")
+                os.makedirs(d, exist_ok=True)
+                torch.save({"model": net.state_dict(), "ema": ema.state_dict(), "opt": ts.state_dict(), "args": args},
+                           os.path.join(d, f"{step:07d}.pt"))
+            if world > 1:
+                dist.barrier()
     if world > 1:
         dist.destroy_process_group()
 

@@ -106,12 +106,29 @@ def make_batches(n, B, R, ncls, seed=0):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_train(B, steps, warmup, R=32, threads=None):
-    """The reference's algorithm on the host CPU (oracle port, fp32, AdamW): samples/s.  Checker code timed as a
-    BASELINE only — never on the product path."""
+def pin_to_one_socket():
+    """CPU baseline stability (the CPU arm moved 13x between runs): bind this process to the physical cores
+    of socket 0 (one hardware thread per core) and size torch's pool to match.  Returns (threads, description)."""
+    try:
+        cores = {}
+        for c in sorted(os.sched_getaffinity(0)):
+            base = f"/sys/devices/system/cpu/cpu{c}/topology/"
+            pkg = int(open(base + "physical_package_id").read())
+            core = int(open(base + "core_id").read())
+            cores.setdefault(pkg, {}).setdefault(core, c)     # first hardware thread of every physical core
+        pkg0 = min(cores)
+        cpus = sorted(cores[pkg0].values())
+        os.sched_setaffinity(0, cpus)
+        torch.set_num_threads(len(cpus))
+        return len(cpus), f"pinned to the {len(cpus)} physical cores of socket {pkg0} (of {len(cores)} sockets)"
+    except Exception as e:  # no sysfs topology: leave the affinity alone
+        return torch.get_num_threads(), f"unpinned ({type(e).__name__})"
+
+
+def cpu_reference_train(B, steps, warmup, R=32):
+    """The reference's algorithm on the host CPU (oracle port, fp32, AdamW(wd=0)): samples/s.  Checker code timed as a
+    BASELINE only — never on the product path.  SURVEY 8(d): full train step at B=8, 1 warm-up + 3 timed."""
     from oracle import maskdit_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
     cfg = O.Cfg(model_type="DiT-XL/2", img_resolution=R, num_classes=1000)
     sd = {k: v.requires_grad_(not k.endswith("pos_embed")) for k, v in O.make_state_dict(cfg, 1).items()}
     m = {k: torch.zeros_like(v) for k, v in sd.items() if v.requires_grad}
@@ -135,26 +152,89 @@ def cpu_reference_train(B, steps, warmup, R=32, threads=None):
     return B * len(times) / sum(times), sum(times)
 
 
+def cpu_baseline_record(steps, warmup, R=32, B=8):
+    threads, how = pin_to_one_socket()
+    sps, secs = cpu_reference_train(B, steps, warmup, R=R)
+    return sps, secs, {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "same_config": False,
+                       "sample": f"{steps} timed steps (+{warmup} warm-up) of batch {B} (SURVEY 8d), EDM loss fwd + bwd + "
+                                 f"AdamW, torch CPU fp32, {threads} threads {how}; host has {os.cpu_count()} logical "
+                                 f"CPUs; {secs:.1f} s timed.  /root/reference is not on the GPU box: the oracle port "
+                                 "(pinned to the unmodified reference by tests/golden) is what runs"}
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    B = 2
-    cores = os.cpu_count()
-    sps, secs = cpu_reference_train(B, args.steps, args.warmup, R=32 if args.workload == "train256" else 64)
+    R = 64 if args.workload == "train512" else 32
+    B = 8 if R == 32 else 2
+    sps, secs, rec = cpu_baseline_record(args.steps, max(1, min(args.warmup, 2)), R=R, B=B)
     line = {"impl": "reference", "metric": "train_samples_per_sec", "value": sps, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "MaskDiT-XL/2 ImageNet-256 train step (32x32x4 latents, mask 0.5) on host CPU",
-                       "batch_per_step": B},
-            "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps of batch {B} (fwd+bwd+AdamW), torch CPU fp32, "
-                                       f"{torch.get_num_threads()} threads; /root/reference is not on the GPU box, so "
-                                       "the oracle port (pinned to the reference by tests/golden) is what is timed"},
+            "config": {"workload": f"MaskDiT-XL/2 ImageNet-{256 if R == 32 else 512} train step ({R}x{R}x4 latents, "
+                                   "mask 0.5) on host CPU", "batch_per_step": B, "same_config": False},
+            "cpu_baseline": rec,
             "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+def gemm_traffic():
+    """DRAM read+write bytes per GEMM launch from the committed `ncu --set full` capture (never a constant in code)."""
+    for name in ("r02_gemm_ncu_full.json", "r01_gemm_ncu_full_v3.json"):
+        f = os.path.join(ROOT, "profiles", name)
+        try:
+            d = json.load(open(f))
+            rows = d["launches"] if isinstance(d, dict) else d
+            vals = [r["dram_bytes"] if "dram_bytes" in r else 1e6 * (r["dram_read_MB"] + r["dram_write_MB"])
+                    for r in rows if "dram_bytes" in r or "dram_read_MB" in r]
+            if vals:
+                return sum(vals) / len(vals), f"profiles/{name} (mean of {len(vals)} launches inside a step)"
+        except Exception:
+            continue
+    return None, "no ncu --set full capture found under profiles/"
+
+
 # ---------------------------------------------------------------------------------------------------------------
+def build_xl2(R, dev):
+    from maskdit_b200.maskdit import Precond_models
+    torch.manual_seed(0)
+    net = Precond_models["edm"](img_resolution=R, img_channels=4, num_classes=1000, model_type="DiT-XL/2",
+                                use_decoder=True, mae_loss_coef=0.1, pad_cls_token=False)
+    randomise_zero_init(net)
+    return net.to(dev)
+
+
+class Env:
+    def __init__(self, dev, world, rank):
+        self.dev, self.world, self.rank = dev, world, rank
+
+    def sync_all(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.world == 1:
+            return ms
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, K):
+        """K calls of fn bracketed by barrier + synchronize on both sides, CUDA events on the launching stream, max
+        over ranks (ms)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.sync_all()
+        e0.record()
+        for i in range(K):
+            fn(i)
+        e1.record()
+        self.sync_all()
+        return self.max_over_ranks(e0.elapsed_time(e1))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,6 +244,8 @@ def main():
     ap.add_argument("--workload", default="train256", choices=["train256", "train512", "sampler"])
     ap.add_argument("--batch-per-gpu", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true",
+                    help="skip the sub-records (BASELINE configs 3-5: 128/GPU, 64x64x4 latents, sampler)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -174,37 +256,34 @@ def main():
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
 
     import torch.distributed as dist
-    from maskdit_b200 import _lib
-    from maskdit_b200.maskdit import Precond_models
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     PK = peaks()
+    env = Env(dev, world, rank)
 
     R = 64 if args.workload == "train512" else 32
-    torch.manual_seed(0)
-    net = Precond_models["edm"](img_resolution=R, img_channels=4, num_classes=1000, model_type="DiT-XL/2",
-                                use_decoder=True, mae_loss_coef=0.1, pad_cls_token=False)
-    randomise_zero_init(net)
-    net = net.to(dev)
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+    net = build_xl2(R, dev)
     if args.workload == "sampler":
-        line = bench_sampler(args, net, dev, world, rank, PK, sync_all, max_over_ranks)
+        line = bench_sampler(args, net, env, PK)
     else:
-        line = bench_train(args, net, dev, world, rank, R, PK, sync_all, max_over_ranks)
+        line = bench_train(args, net, env, R, PK, args.batch_per_gpu or (256 if R == 32 else 128), args.steps,
+                           args.warmup, full=True)
+        if args.workload == "train256" and not args.no_sub and args.batch_per_gpu is None:
+            # BASELINE.json configs 3, 4, 5 next to the headline (config 2), same process, same box, same clocks
+            sub = {}
+            sub["c3_global1024_at_8gpu"] = bench_train(args, net, env, 32, PK, 128, max(5, args.steps // 2), 3, full=False)
+            sub["c5_sampler"] = bench_sampler(args, net, env, PK, iters=2, warm=1)
+            del net
+            torch.cuda.empty_cache()
+            net64 = build_xl2(64, dev)
+            sub["c4_512px"] = bench_train(args, net64, env, 64, PK, 128, max(4, args.steps // 4), 3, full=False)
+            del net64
+            torch.cuda.empty_cache()
+            line["sub"] = sub
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            _, _, line["cpu_baseline"] = cpu_baseline_record(3, 1, R=R, B=8 if R == 32 else 2)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -212,12 +291,14 @@ def main():
         dist.destroy_process_group()
 
 
-def bench_train(args, net, dev, world, rank, R, PK, sync_all, max_over_ranks):
+def bench_train(args, net, env, R, PK, B, steps, warmup, full):
+    """One training-step measurement.  full=True: the headline record (resident + e2e + per-launch GEMM timing +
+    clocks); full=False: a compact sub-record (resident inputs only)."""
     import copy
 
     from maskdit_b200 import _lib
     from maskdit_b200.train_step import TrainStep
-    B = args.batch_per_gpu or (256 if R == 32 else 128)
+    dev, world, rank = env.dev, env.world, env.rank
     net.train()
     ema = copy.deepcopy(net).eval()
     ts = TrainStep(net, ema, lr=1e-4, global_batch=B * world, overlap=os.environ.get("MDT_OVERLAP", "0") == "1")
@@ -236,50 +317,56 @@ def bench_train(args, net, dev, world, rank, R, PK, sync_all, max_over_ranks):
         loss = ts.step(x, y, 0.5, 0.1)
         loss_host.copy_(loss.mean().reshape(1), non_blocking=True)   # D2H read of the step's result
 
-    def timed(fn, K):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sync_all()
-        e0.record()
-        for i in range(K):
-            fn(i)
-        e1.record()
-        sync_all()
-        return max_over_ranks(e0.elapsed_time(e1))
-
-    for i in range(args.warmup):
+    for i in range(warmup):
         step_resident(i)
     clocks = ClockSampler(torch.cuda.current_device())
-    if rank == 0:
+    if rank == 0 and full:
         clocks.start()
     n0 = _lib.LAUNCHES
-    ms = timed(step_resident, args.steps)
+    ms = env.timed(step_resident, steps)
     launches = _lib.LAUNCHES - n0
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop() if (rank == 0 and full) else None
+    ms_step = ms / steps
+    sps = B * world * steps / (ms / 1e3)
+    flop = FLOP_PER_SAMPLE[256 if R == 32 else 512]
+    step_tf = sps / world * flop / 1e12
+    workload = (f"MaskDiT-XL/2 ImageNet-{256 if R == 32 else 512} training step ({R}x{R}x4 latents, bf16 GEMM operands / "
+                f"fp32 accumulate+residual, mask_ratio 0.5, EDM+MAE loss, AdamW+EMA)")
+    if not full:
+        rec = {"metric": "train_samples_per_sec", "value": sps, "unit": "samples/s", "n_gpus": world, "steps": steps,
+               "warmup": warmup, "ms_per_step": ms_step, "gpu_launches": launches,
+               "config": {"workload": workload, "batch_per_gpu": B, "global_batch": B * world},
+               "roofline": {"bound": "tensor", "step_achieved": step_tf, "peak": PK["sustained"], "unit": "TFLOP/s",
+                            "step_frac": step_tf / PK["sustained"], "peak_source": f"{PK['src']} sustained bf16"}}
+        del ts, ema, resident
+        torch.cuda.empty_cache()
+        return rec
     for i in range(2):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = env.timed(step_e2e, steps)
     final_loss = float(loss_host.item())
 
     # dominant kernel (the tcgen05 GEMM family) timed per launch with CUDA events inside one real step
+    # (the C++ step driver issues the GEMMs itself, so this ONE extra step runs the identical launch sequence through the
+    # kernel-by-kernel Python engine, whose gemm() wrapper brackets every launch with events on the launching stream)
+    from maskdit_b200.engine import Engine
+    c_engine, net._engine = net._engine, Engine(net._cfg(), net.flat_store())
     _lib.GEMM_PROFILE = []
     step_resident(0)
     torch.cuda.synchronize()
     prof, _lib.GEMM_PROFILE = _lib.GEMM_PROFILE, None
+    net._engine = c_engine
     gemm_ms = sum(a.elapsed_time(b) for _, a, b, _k in prof)
     gemm_flops = sum(f for f, _, _, _k in prof)
-    ms_step = ms / args.steps
-    sps = B * world * args.steps / (ms / 1e3)
-    sps_e2e = B * world * args.steps / (ms_e2e / 1e3)
-    flop = FLOP_PER_SAMPLE[256 if R == 32 else 512]
+    sps_e2e = B * world * steps / (ms_e2e / 1e3)
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic, traffic_src = gemm_traffic() if (R == 32 and B == 256) else (None, "no capture for this configuration")
     line = {
-        "metric": "train_samples_per_sec", "value": sps, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "metric": "train_samples_per_sec", "value": sps, "unit": "samples/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"MaskDiT-XL/2 ImageNet-{256 if R == 32 else 512} training step "
-                               f"({R}x{R}x4 latents, bf16 GEMM operands / fp32 accumulate+residual, mask_ratio 0.5, "
-                               f"EDM+MAE loss, AdamW+EMA)",
-                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+        "config": {"workload": workload, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "grad_allreduce": ts.describe_collective(),
                    "l2_policy": "per-step working set (activations > 40 GB) far exceeds the 126 MB L2; no flush needed",
                    "final_loss": final_loss},
         "clocks": clk,
@@ -288,25 +375,20 @@ def bench_train(args, net, dev, world, rank, R, PK, sync_all, max_over_ranks):
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all GEMM launches of one step)",
                      "achieved": achieved, "peak": PK["sustained"], "unit": "TFLOP/s",
                      "frac": achieved / PK["sustained"], "peak_source": f"{PK['src']} sustained bf16",
-                     # DRAM read+write bytes per launch from the committed `ncu --set full` capture of four consecutive
-                     # launches of this kernel inside a step (profiles/r01_gemm_ncu_full_v3.json: 647, 751, 268,
-                     # 420 MB against 690, 690, 310, 456 MB algorithmic) - average, bytes
-                     "traffic": 521e6 if R == 32 and B == 256 else None,
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "launches_per_step": len(prof), "share_of_step": gemm_ms / ms_step,
-                     "step_achieved": sps / world * flop / 1e12, "step_frac": sps / world * flop / 1e12 / PK["sustained"]},
+                     "step_achieved": step_tf, "step_frac": step_tf / PK["sustained"]},
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb, secs = cpu_reference_train(2, 4, 1, R=R)
-        line["cpu_baseline"] = {"value": cb, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"4 timed steps (+1 warm-up) of batch 2, fwd+bwd+AdamW, torch CPU fp32, "
-                                          f"{torch.get_num_threads()} threads ({secs:.1f} s)"}
+    del ts, ema, resident
+    torch.cuda.empty_cache()
     return line
 
 
-def bench_sampler(args, net, dev, world, rank, PK, sync_all, max_over_ranks):
+def bench_sampler(args, net, env, PK, iters=None, warm=None):
     from maskdit_b200 import _lib
     from maskdit_b200.sampler import edm_sampler
-    B = args.batch_per_gpu or 64
+    dev, world, rank = env.dev, env.world, env.rank
+    B = (args.batch_per_gpu if args.workload == "sampler" else None) or 64
     net.eval()
     g = torch.Generator().manual_seed(rank)
     lat_h = torch.randn(B, 4, 32, 32, generator=g).pin_memory()
@@ -319,25 +401,19 @@ def bench_sampler(args, net, dev, world, rank, PK, sync_all, max_over_ranks):
                             num_steps=18)
             out_h.copy_(z, non_blocking=True)
 
-    for i in range(max(1, args.warmup // 3)):
+    W = warm if warm is not None else max(1, args.warmup // 3)
+    for i in range(W):
         run(i)
-    K = max(1, args.steps // 5)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    K = iters if iters is not None else max(1, args.steps // 5)
     clocks = ClockSampler(torch.cuda.current_device())
     if rank == 0:
         clocks.start()
-    sync_all()
     n0 = _lib.LAUNCHES
-    e0.record()
-    for i in range(K):
-        run(i)
-    e1.record()
-    sync_all()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms = env.timed(run, K)
     ips = B * world * K / (ms / 1e3)
     ach = ips / world * SAMPLER_FLOP_PER_IMAGE / 1e12
     return {"metric": "edm_sampler_imgs_per_sec", "value": ips, "unit": "img/s", "n_gpus": world, "steps": K,
-            "warmup": max(1, args.warmup // 3), "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "EDM sampler 18 steps (35 net evals), CFG 1.5, 32x32x4 latents, MaskDiT-XL/2",
                        "batch_per_gpu": B, "parallelism": f"replicas x{world}"},

@@ -29,6 +29,9 @@ const char* mdt_status_string(int status);
 int mdt_abi_version(void);
 /* BLOCK_N * 10 + CTAs-per-tile (1 or 2 = tcgen05 cta_group::2 SM pair) of the last mdt_gemm_bf16 launch (tests). */
 int mdt_gemm_last_config(void);
+/* Bit set of the GEMM instances launched since the last reset: bit (BLOCK_N/64 - 2) * 2 + (CTAs - 1), i.e. 128/1 = 0,
+ * 128/2 = 1, 192/1 = 2, 192/2 = 3, 256/1 = 4, 256/2 = 5.  reset != 0 clears it after reading.                        */
+int mdt_gemm_configs_seen(int reset);
 
 /* ------------------------------------------------------------------------------------------------------------
  * bf16 tensor-core GEMM (tcgen05 / TMEM / TMA):  out[M,N] (+)= sum_k A[m,k] * B[n,k], fp32 accumulate.
@@ -148,6 +151,9 @@ int mdt_attention_bwd(const void* qkv, const void* out, const void* dout, const 
  * With MDT_ATTN_STRICT=1 in the environment a shape no tcgen05 kernel accepts returns MDT_ERR_UNSUPPORTED instead
  * of running the mma.sync kernels.                                                                             */
 int mdt_attention_last_impl(int which);
+/* Log of every attention call since the last reset, 4 ints per call: (which, T, head_dim, kernel family).  Returns
+ * the number of entries copied (<= cap); out4 == NULL resets the log.  The step driver's internal calls are logged too. */
+int mdt_attention_impl_log(int* out4, int cap);
 
 /* ------------------------------------------------------------------------------------------------------------
  * unmask_tokens + decoder_pos_embed (models/maskdit.py:157-163,543-545):
@@ -218,6 +224,76 @@ int mdt_to_uint8_nhwc(const float* img, unsigned char* out, int B, int C, int H,
 int mdt_adamw_ema(float* w, const float* g, float* m, float* v, float* ema, void* w_bf16, long long n, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int step, float ema_decay,
                   float grad_scale, int max_blocks, void* stream);
+/* Same with a bf16 gradient operand: the buffer a bf16 gradient all-reduce produced (1.46 GB instead of
+ * 2.92 GB on the wire, fp32 moments / master weights unchanged).                                                  */
+int mdt_adamw_ema_g16(float* w, const void* g_bf16, float* m, float* v, float* ema, void* w_bf16, long long n,
+                      float lr, float beta1, float beta2, float eps, float weight_decay, int step, float ema_decay,
+                      float grad_scale, int max_blocks, void* stream);
+
+/* Cap on the SMs the persistent kernels (tcgen05 GEMM, persistent attention backward) occupy: n > 0 sizes their grids
+ * for n SMs instead of the device's count, leaving the rest to a concurrently running collective (the gradient
+ * all-reduce overlapped with the backward); 0 = whole device.  Host-side setting, read at launch.                  */
+int mdt_set_sm_budget(int n);
+int mdt_get_sm_budget(void);
+
+/* ============================================================================================================
+ * Step driver: the whole network forward / backward as ONE call each over a packed parameter blob and ONE
+ * caller-provided workspace — the launch sequence the reference obtains from autograd + torch.compile for
+ * `loss = loss_fn(net, ...); loss.mean().backward()` (train.py:179,216-220; DiT.forward models/maskdit.py:467-557).
+ * No allocation, no host synchronisation, everything enqueued on `stream`.
+ *
+ * Packed blob (element offsets shared by the fp32 master w32, the bf16 shadow w16 and the fp32 gradient):
+ *   [adaLN_modulation.1.weight of blocks 0..depth-1, decoder_layer, decoder_blocks 0.., final_layer]
+ *   [the matching adaLN biases] [all other trainable tensors in registration order] [pos_embed, decoder_pos_embed]
+ * every tensor on a 64-element boundary; names = the reference's state-dict keys (models/maskdit.py:242-332).
+ * ============================================================================================================ */
+typedef struct mdt_model_cfg {
+  int img_resolution, img_channels, patch_size, num_classes; /* EDMPrecond / DiT ctor, models/maskdit.py:722-741     */
+  int hidden, depth, heads, mlp_hidden;                      /* encoder DiTBlocks (DiT_models, :645-715)              */
+  int dec_hidden, dec_depth, dec_heads, dec_mlp_hidden;      /* decoder (:310-312: 512, 8, 16, 2048)                  */
+  int has_mask_token;                                        /* mae_loss_coef > 0 (:297-299)                          */
+  float sigma_data;
+} mdt_model_cfg;
+typedef struct mdt_model mdt_model; /* host-side layout object: no device memory, no CUDA calls */
+
+int mdt_model_create(const mdt_model_cfg* cfg, mdt_model** out);
+void mdt_model_destroy(mdt_model* m);
+long long mdt_model_param_count(const mdt_model* m, int trainable_only); /* blob length in elements                  */
+int mdt_model_num_tensors(const mdt_model* m);
+/* i-th tensor in BLOB order: state-dict key, element offset, element count                                            */
+int mdt_model_param_info(const mdt_model* m, int i, char* name, int name_cap, long long* offset, long long* numel);
+int mdt_model_mod_width(const mdt_model* m); /* columns of the concatenated adaLN modulation vector                   */
+
+/* Workspace bytes for batch B with T kept tokens per sample (T <= 0: no token dropping, T = L).
+ * training != 0: every activation the backward needs stays resident (+ the backward's scratch); else inference.       */
+long long mdt_workspace_bytes(const mdt_model* m, int B, int T, int training);
+
+/* F [B*L, p*p*C] f32 = DiT.forward on x_in [B,C,R,R] (UNscaled network input, c_in applied inside), sigma [B],
+ * labels [B,num_classes] f32 (NULL iff num_classes == 0), ids_keep [B,T] / ids_restore [B,L] int64 (both NULL: all
+ * tokens).  save != 0 keeps the activations in `workspace` (256-byte aligned) for mdt_backward.                        */
+int mdt_forward(const mdt_model* m, const float* w32, const void* w16, const float* x_in, const float* sigma,
+                const float* labels, const int64_t* ids_keep, const int64_t* ids_restore, int B, int T, int save,
+                void* workspace, long long workspace_bytes, float* F_out, void* stream);
+
+/* grad (flat f32, blob offsets, trainable region) += d(loss)/d(params) given dF [B*L, p*p*C] bf16 and the workspace
+ * of the matching mdt_forward(save = 1).  `on_ready(user, lo, hi)` (may be NULL) is called on the host as soon as the
+ * kernels that finalise the gradient elements [lo, hi) of one block have been enqueued (DDP-bucket-style overlap).     */
+typedef void (*mdt_grad_ready_fn)(void* user, long long lo, long long hi);
+int mdt_backward(const mdt_model* m, const float* w32, const void* w16, float* grad, const float* x_in,
+                 const float* sigma, const int64_t* ids_keep, const int64_t* ids_restore, const void* dF_bf16, int B,
+                 int T, void* workspace, long long workspace_bytes, mdt_grad_ready_fn on_ready, void* user,
+                 void* stream);
+
+/* Data-parallel gradient exchange (train.py:178 DDP -> SURVEY 8e: ONE sum-all-reduce of the flat gradient buffer over
+ * NVLink).  NCCL is resolved at run time from the process's libnccl.so.2 (MDT_ERR_DRIVER when absent).
+ *   mdt_nccl_unique_id: rank 0 fills 128 bytes, the host code ships them to every rank (any side channel);
+ *   mdt_nccl_comm_create: ncclCommInitRank (max_ctas > 0: ncclCommInitRankConfig with maxCTAs, a communicator that
+ *   shares the GPU with the backward, see mdt_set_sm_budget); mdt_allreduce_grads: in-place SUM of fp32 (bf16 = 0) or
+ *   bf16 elements.                                                                                                  */
+int mdt_nccl_unique_id(void* id128);
+int mdt_nccl_comm_create(const void* id128, int rank, int world, int max_ctas, void** comm);
+int mdt_nccl_comm_destroy(void* comm);
+int mdt_allreduce_grads(void* comm, void* grad, long long n, int bf16, void* stream);
 
 #ifdef __cplusplus
 }

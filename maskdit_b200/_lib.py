@@ -36,6 +36,18 @@ class GemmArgs(Structure):
     ]
 
 
+class ModelCfg(Structure):
+    """mdt_model_cfg (include/maskdit_b200.h)."""
+    _fields_ = [
+        ("img_resolution", c_int), ("img_channels", c_int), ("patch_size", c_int), ("num_classes", c_int),
+        ("hidden", c_int), ("depth", c_int), ("heads", c_int), ("mlp_hidden", c_int),
+        ("dec_hidden", c_int), ("dec_depth", c_int), ("dec_heads", c_int), ("dec_mlp_hidden", c_int),
+        ("has_mask_token", c_int), ("sigma_data", c_float),
+    ]
+
+
+GRAD_READY_FN = ctypes.CFUNCTYPE(None, c_void_p, c_longlong, c_longlong)
+
 EPI_STORE, EPI_GELU, EPI_GATE_RESID, EPI_DGELU, EPI_ATOMIC = range(5)
 ACT_NONE, ACT_SILU = 0, 1
 
@@ -61,6 +73,8 @@ _SIGS = {
     "mdt_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _P],
     "mdt_attention_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mdt_attention_last_impl": [_I],
+    "mdt_attention_impl_log": [_P, _I],
+    "mdt_gemm_configs_seen": [_I],
     "mdt_gemm_last_config": [],
     "mdt_unmask_tokens": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mdt_unmask_tokens_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
@@ -72,6 +86,20 @@ _SIGS = {
     "mdt_heun_update": [_I, _P, _P, _P, _P, _P, _D, _D, _LL, _P],
     "mdt_lincomb_f64": [_D, _P, _D, _P, _D, _P, _P, _P, _D, _LL, _P],
     "mdt_to_uint8_nhwc": [_P, _P, _I, _I, _I, _I, _P],
+    # step driver (csrc/driver.cu)
+    "mdt_model_create": [POINTER(ModelCfg), POINTER(c_void_p)],
+    "mdt_model_num_tensors": [_P],
+    "mdt_model_param_info": [_P, _I, c_char_p, _I, POINTER(c_longlong), POINTER(c_longlong)],
+    "mdt_model_mod_width": [_P],
+    "mdt_forward": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _LL, _P, _P],
+    "mdt_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _LL, GRAD_READY_FN, _P, _P],
+    "mdt_nccl_unique_id": [_P],
+    "mdt_nccl_comm_create": [_P, _I, _I, _I, POINTER(c_void_p)],
+    "mdt_nccl_comm_destroy": [_P],
+    "mdt_allreduce_grads": [_P, _P, _LL, _I, _P],
+    "mdt_adamw_ema_g16": [_P, _P, _P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _F, _I, _P],
+    "mdt_set_sm_budget": [_I],
+    "mdt_get_sm_budget": [],
     "mdt_adamw_ema": [_P, _P, _P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _F, _I, _P],
 }
 
@@ -88,6 +116,12 @@ def lib():
         L.mdt_status_string.restype = c_char_p
         L.mdt_status_string.argtypes = [c_int]
         L.mdt_abi_version.restype = c_int
+        L.mdt_model_destroy.restype = None
+        L.mdt_model_destroy.argtypes = [c_void_p]
+        L.mdt_model_param_count.restype = c_longlong
+        L.mdt_model_param_count.argtypes = [c_void_p, c_int]
+        L.mdt_workspace_bytes.restype = c_longlong
+        L.mdt_workspace_bytes.argtypes = [c_void_p, c_int, c_int, c_int]
         for name, sig in _SIGS.items():
             if not hasattr(L, name) and os.environ.get("MDT_ALLOW_PARTIAL_LIB") == "1":
                 continue  # development only: probing a partially built library
@@ -99,7 +133,8 @@ def lib():
 
 
 def exported_symbols():
-    return ["mdt_status_string", "mdt_abi_version", *_SIGS.keys()]
+    return ["mdt_status_string", "mdt_abi_version", "mdt_model_destroy", "mdt_model_param_count",
+            "mdt_workspace_bytes", *_SIGS.keys()]
 
 
 LAUNCHES = 0  # kernels launched through the C ABI (bench.py reports it as gpu_launches)

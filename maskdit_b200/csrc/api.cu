@@ -1,7 +1,10 @@
 // extern "C" surface that is not tied to one kernel file: status strings, ABI version, GEMM entry.
 #include "gemm.h"
 
-namespace mdt { extern int g_gemm_last_config; }
+namespace mdt {
+extern int g_gemm_last_config, g_gemm_configs_seen;
+int g_sm_budget = 0;  // mdt_set_sm_budget: SMs the persistent kernels may occupy (0 = all)
+}
 
 extern "C" {
 
@@ -19,7 +22,19 @@ const char* mdt_status_string(int status) {
 
 int mdt_abi_version(void) { return 1; }
 
+int mdt_set_sm_budget(int n) {
+  if (n < 0) return MDT_ERR_ARG;
+  mdt::g_sm_budget = n;
+  return MDT_OK;
+}
+int mdt_get_sm_budget(void) { return mdt::g_sm_budget; }
+
 int mdt_gemm_last_config(void) { return mdt::g_gemm_last_config; }
+int mdt_gemm_configs_seen(int reset) {
+  const int v = mdt::g_gemm_configs_seen;
+  if (reset) mdt::g_gemm_configs_seen = 0;
+  return v;
+}
 
 int mdt_gemm_bf16(const mdt_gemm_args* args, void* stream) {
   if (!args || !args->A || !args->B || !args->out) return MDT_ERR_ARG;

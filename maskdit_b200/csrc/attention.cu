@@ -418,6 +418,16 @@ static int dp_of(int dh) {
 // tcgen05 (attention_tc.cu), 3 = blocked split-tile tcgen05 (attention_sw_long.cu), 4 = blocked no-swizzle tcgen05
 // (attention_tc_long.cu).  MDT_ATTN_STRICT=1: a shape none of the tcgen05 paths accepts is an error, not a fallback.
 static int g_attn_last_impl[2] = {-1, -1};
+constexpr int kAttnLogCap = 1024;
+static int g_attn_log[kAttnLogCap][4];  // (which, T, head_dim, impl) of every call since the last reset
+static int g_attn_log_n = 0;
+static void attn_log(int which, int T, int dh, int impl) {
+  g_attn_last_impl[which] = impl;
+  if (g_attn_log_n < kAttnLogCap) {
+    int* e = g_attn_log[g_attn_log_n++];
+    e[0] = which, e[1] = T, e[2] = dh, e[3] = impl;
+  }
+}
 static bool attn_strict() {
   static const bool on = [] { const char* e = getenv("MDT_ATTN_STRICT"); return e && e[0] == '1'; }();
   return on;
@@ -426,7 +436,7 @@ static bool attn_strict() {
   {                                                                      \
     const int rc_ = (CALL);                                              \
     if (rc_ != MDT_ERR_UNSUPPORTED) {                                    \
-      if (rc_ == MDT_OK) g_attn_last_impl[WHICH] = IMPL;                 \
+      if (rc_ == MDT_OK) attn_log(WHICH, T, dh, IMPL);                   \
       return rc_;                                                        \
     }                                                                    \
   }
@@ -434,6 +444,17 @@ static bool attn_strict() {
 extern "C" {
 
 int mdt_attention_last_impl(int which) { return (which == 0 || which == 1) ? g_attn_last_impl[which] : -1; }
+
+int mdt_attention_impl_log(int* out4, int cap) {
+  if (!out4) {  // reset
+    g_attn_log_n = 0;
+    return 0;
+  }
+  const int n = g_attn_log_n < cap ? g_attn_log_n : cap;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < 4; ++j) out4[4 * i + j] = g_attn_log[i][j];
+  return n;
+}
 
 int mdt_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int dh, void* stream) {
   if (!qkv || !out || B <= 0 || T <= 0 || H <= 0) return MDT_ERR_ARG;
@@ -452,7 +473,7 @@ int mdt_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int 
     }
     if (attn_strict()) return MDT_ERR_UNSUPPORTED;
   }
-  g_attn_last_impl[0] = 0;
+  attn_log(0, T, dh, 0);
   MDT_DP_DISPATCH(dp, attn_fwd_kernel<kDP><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
                           static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, T, H, dh,
                           scale));
@@ -478,7 +499,7 @@ int mdt_attention_bwd(const void* qkv, const void* out, const void* dout, const 
     }
     if (attn_strict()) return MDT_ERR_UNSUPPORTED;
   }
-  g_attn_last_impl[1] = 0;
+  attn_log(1, T, dh, 0);
   MDT_DP_DISPATCH(dp, {
     attn_bwd_dq_kernel<kDP><<<grid, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv),
                                                   static_cast<const __nv_bfloat16*>(out),

@@ -21,6 +21,7 @@
 #include "gemm.h"
 
 namespace mdt {
+extern int g_sm_budget;  // api.cu: SMs the persistent kernels may occupy (0 = all)
 
 constexpr int sw_fwd_v_offset(int dp, int tk) {
   const int qk = (kQB + tk) * dp * 2, pb = kQB * tk * 2;
@@ -627,7 +628,8 @@ static int launch_sw_bwd(const void* qkv, const void* dout, const float* lse, vo
     }
   }
   const int nitems = B * H;
-  kern<<<nitems < sms ? nitems : sms, kSwBwdThreads, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], lse, H, dh,
+  const int grid_sms = (g_sm_budget > 0 && g_sm_budget < sms) ? g_sm_budget : sms;   // mdt_set_sm_budget
+  kern<<<nitems < grid_sms ? nitems : grid_sms, kSwBwdThreads, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], lse, H, dh,
                                                                  scale, nitems);
   return cudaGetLastError() == cudaSuccess ? MDT_OK : MDT_ERR_CUDA;
 }
@@ -656,7 +658,8 @@ static int launch_sw_bwd2(const void* qkv, const void* out, const void* dout, co
     if (rc != MDT_OK) return rc;
   }
   const int nitems = B * H;
-  attn_sw_bwd2_kernel<<<nitems < sms ? nitems : sms, kSwBwdThreads, smem, st>>>(tm[0], tm[1], tm[2], tm[3], lse, H,
+  const int grid_sms = (g_sm_budget > 0 && g_sm_budget < sms) ? g_sm_budget : sms;
+  attn_sw_bwd2_kernel<<<nitems < grid_sms ? nitems : grid_sms, kSwBwdThreads, smem, st>>>(tm[0], tm[1], tm[2], tm[3], lse, H,
                                                                                 scale, nitems);
   return cudaGetLastError() == cudaSuccess ? MDT_OK : MDT_ERR_CUDA;
 }

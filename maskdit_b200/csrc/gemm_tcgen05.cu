@@ -575,8 +575,9 @@ int make_token_tile_tmap(void* m, const void* ptr, unsigned long long rows, unsi
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MDT_OK : MDT_ERR_TMAP;
 }
+extern int g_sm_budget;
 static int g_num_sms = 0;
-static int num_sms() {
+static int num_sms_device() {
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -585,8 +586,15 @@ static int num_sms() {
   }
   return g_num_sms;
 }
+// SMs the persistent grid is sized for: the device's, or the budget set by mdt_set_sm_budget (rounded down to even so
+// that SM pairs stay whole)
+static int num_sms() {
+  const int n = num_sms_device();
+  if (g_sm_budget > 0 && g_sm_budget < n) return g_sm_budget >= 2 ? (g_sm_budget & ~1) : 2;
+  return n;
+}
 
-extern int g_gemm_last_config;
+extern int g_gemm_last_config, g_gemm_configs_seen;
 template <int BLOCK_N, bool A_MN, bool B_MN, int CG>
 static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, CG>;
@@ -646,10 +654,12 @@ static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
   cfg.attrs = attr, cfg.numAttrs = 1;
   if (cudaLaunchKernelEx(&cfg, kern, ta, tb, p) != cudaSuccess) return MDT_ERR_CUDA;
   g_gemm_last_config = BLOCK_N * 10 + CG;
+  g_gemm_configs_seen |= 1 << ((BLOCK_N / 64 - 2) * 2 + (CG - 1));
   return cudaGetLastError() == cudaSuccess ? MDT_OK : MDT_ERR_CUDA;
 }
 
 int g_gemm_last_config = 0;  // BLOCK_N * 10 + CG of the last launch (tests assert the 2-CTA instances ran)
+int g_gemm_configs_seen = 0;  // bit (BLOCK_N/64 - 2) * 2 + (CG - 1) per instance launched since the last reset
 static int g_force_cg = 0;  // 0 = auto, 1 / 2 = forced (MDT_GEMM_CG env, for A/B measurements)
 
 template <bool A_MN, bool B_MN>

@@ -189,15 +189,22 @@ __global__ void to_uint8_nhwc_kernel(const float* __restrict__ img, unsigned cha
 }
 
 // Fused AdamW + EMA + bf16 shadow, float4-vectorised over flat buffers.
+template <bool G16>  // G16: the gradient operand is bf16 (the buffer a bf16 all-reduce produced), else fp32
 __global__ void __launch_bounds__(256)
-adamw_ema_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+adamw_ema_kernel(float* __restrict__ w, const void* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  float* __restrict__ ema, __nv_bfloat16* __restrict__ w16, long long n, float lr, float b1, float b2,
                  float eps, float wd, float inv_bc1, float inv_bc2, float ema_decay, float gscale) {
   const long long n4 = n >> 2;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
     float4 wv = reinterpret_cast<float4*>(w)[i];
-    float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 gv;
+    if constexpr (G16) {
+      const uint2 u = reinterpret_cast<const uint2*>(g)[i];
+      gv = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+    } else {
+      gv = reinterpret_cast<const float4*>(g)[i];
+    }
     float4 mv = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
     float* wp = &wv.x;
@@ -344,19 +351,34 @@ int mdt_to_uint8_nhwc(const float* img, unsigned char* out, int B, int C, int H,
   return launch_status();
 }
 
-int mdt_adamw_ema(float* w, const float* g, float* m, float* v, float* ema, void* w_bf16, long long n, float lr,
-                  float beta1, float beta2, float eps, float weight_decay, int step, float ema_decay,
-                  float grad_scale, int max_blocks, void* stream) {
+static int adamw_launch(bool g16, float* w, const void* g, float* m, float* v, float* ema, void* w_bf16, long long n,
+                        float lr, float beta1, float beta2, float eps, float weight_decay, int step, float ema_decay,
+                        float grad_scale, int max_blocks, void* stream) {
   if (!w || !g || !m || !v || n <= 0 || step < 1 || (n & 3)) return MDT_ERR_ARG;
   const float inv_bc1 = static_cast<float>(1.0 / (1.0 - pow(static_cast<double>(beta1), step)));
   const float inv_bc2 = static_cast<float>(1.0 / (1.0 - pow(static_cast<double>(beta2), step)));
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;
-  adamw_ema_kernel<<<static_cast<int>(blocks), 256, 0, S(stream)>>>(
-      w, g, m, v, ema, static_cast<__nv_bfloat16*>(w_bf16), n, lr, beta1, beta2, eps, weight_decay, inv_bc1, inv_bc2,
-      ema_decay, grad_scale);
+  auto kern = g16 ? adamw_ema_kernel<true> : adamw_ema_kernel<false>;
+  kern<<<static_cast<int>(blocks), 256, 0, S(stream)>>>(w, g, m, v, ema, static_cast<__nv_bfloat16*>(w_bf16), n, lr,
+                                                        beta1, beta2, eps, weight_decay, inv_bc1, inv_bc2, ema_decay,
+                                                        grad_scale);
   return launch_status();
+}
+
+int mdt_adamw_ema(float* w, const float* g, float* m, float* v, float* ema, void* w_bf16, long long n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, float ema_decay,
+                  float grad_scale, int max_blocks, void* stream) {
+  return adamw_launch(false, w, g, m, v, ema, w_bf16, n, lr, beta1, beta2, eps, weight_decay, step, ema_decay,
+                      grad_scale, max_blocks, stream);
+}
+
+int mdt_adamw_ema_g16(float* w, const void* g_bf16, float* m, float* v, float* ema, void* w_bf16, long long n,
+                      float lr, float beta1, float beta2, float eps, float weight_decay, int step, float ema_decay,
+                      float grad_scale, int max_blocks, void* stream) {
+  return adamw_launch(true, w, g_bf16, m, v, ema, w_bf16, n, lr, beta1, beta2, eps, weight_decay, step, ema_decay,
+                      grad_scale, max_blocks, stream);
 }
 
 int mdt_step_front(const float* moments, const float* eps, const float* rnd_normal, const float* noise_unit,

@@ -309,3 +309,99 @@ class Engine:
         self._wgrad(dqkv, sv["xm1"], 3 * D, D, M, G(f"{p}.attn.qkv.weight"))
         return ops.ln_modulate_bwd_gate(dxm1, sv["X"], sv["mean1"], sv["rstd1"], mod[:, o + D:], NA, T, Gr, True,
                                         dmod[:, o:], dmod[:, o + D:], NA, M, D, gate_next=gate_next)
+
+
+class CEngine:
+    """The same forward / backward issued by the C++ step driver (csrc/driver.cu: `mdt_forward`, `mdt_backward`): ONE
+    C-ABI call each over the packed parameter blob and one workspace buffer, instead of ~780 ctypes calls and a
+    `torch.empty` per activation (70 ms of host time per step in round 1, which bound the 128-samples-per-GPU config).
+    `Engine` above issues the identical launch sequence kernel by kernel and is kept as the cross-check
+    (tests/test_model_gpu_extra.py::test_c_driver_matches_python_engine); MDT_ENGINE=py selects it."""
+
+    def __init__(self, cfg, store):
+        import ctypes
+        self.cfg, self.store = cfg, store
+        L = ops.lib()
+        has_tok = "model.mask_token" in store.offsets
+        h4e = store.offsets["model.blocks.0.mlp.fc1.weight"][2][0] if cfg.depth else 4 * cfg.hidden
+        h4d = store.offsets["model.decoder_blocks.0.mlp.fc1.weight"][2][0] if cfg.dec_depth else 4 * cfg.dec_hidden
+        R = int(round(cfg.num_patches ** 0.5)) * cfg.patch
+        mc = ops.L.ModelCfg(R, cfg.img_channels, cfg.patch, cfg.num_classes, cfg.hidden, cfg.depth, cfg.heads, h4e,
+                            cfg.dec_hidden, cfg.dec_depth, cfg.dec_heads, h4d, int(has_tok), cfg.sigma_data)
+        h = ctypes.c_void_p()
+        ops.check(L.mdt_model_create(ctypes.byref(mc), ctypes.byref(h)), "mdt_model_create", 0)
+        self._h, self._L = h, L
+        # the C driver's packed layout must be the store's: compare every tensor once
+        n = L.mdt_model_num_tensors(h)
+        if n != len(store.offsets):
+            raise ops.L.MdtError(f"driver layout has {n} tensors, the module {len(store.offsets)}")
+        name = ctypes.create_string_buffer(160)
+        off, num = ctypes.c_longlong(), ctypes.c_longlong()
+        for i in range(n):
+            L.mdt_model_param_info(h, i, name, 160, ctypes.byref(off), ctypes.byref(num))
+            k = name.value.decode()
+            if k not in store.offsets or store.offsets[k][:2] != (off.value, num.value):
+                raise ops.L.MdtError(f"driver layout mismatch at {k}: {store.offsets.get(k)} vs {(off.value, num.value)}")
+        if L.mdt_model_param_count(h, 1) != store.n_train or L.mdt_model_param_count(h, 0) != store.n_total:
+            raise ops.L.MdtError("driver blob length differs from the flat store")
+        self.NA = L.mdt_model_mod_width(h)
+        self.launches = {}
+
+    def __del__(self):
+        try:
+            self._L.mdt_model_destroy(self._h)
+        except Exception:
+            pass
+
+    def workspace_bytes(self, B, T, training):
+        n = self._L.mdt_workspace_bytes(self._h, B, T, int(training))
+        if n <= 0:
+            raise ops.L.MdtError("mdt_workspace_bytes failed")
+        return n
+
+    def _count(self, save):
+        """Kernel launches of one forward / backward (for bench.py's gpu_launches claim): same sequence as `Engine`."""
+        c = self.cfg
+        nb = c.depth + c.dec_depth
+        fwd = 12 + (2 if c.num_classes else 0) + 7 * nb          # embed/conditioning 7, decoder layer 3, final 2
+        bwd = 21 + 14 * nb + (1 if c.num_classes else 0)         # final 4, transition 5, patch-embed 1, conditioning 11
+        return fwd, bwd
+
+    def forward(self, x_in, sigma, labels, mask_dict, save):
+        cfg = self.cfg
+        B, L = x_in.shape[0], cfg.num_patches
+        ids_keep = mask_dict["ids_keep"] if mask_dict is not None else None
+        ids_restore = mask_dict["ids_restore"] if mask_dict is not None else None
+        T = ids_keep.shape[1] if ids_keep is not None else L
+        for t, dt in ((x_in, f32), (sigma, f32), (labels, f32), (ids_keep, torch.int64), (ids_restore, torch.int64)):
+            ops._c(t, dt)
+        nbytes = self.workspace_bytes(B, T, save)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x_in.device)   # ONE allocation per pass
+        Fo = torch.empty(B * L, cfg.patch_dim, dtype=f32, device=x_in.device)
+        st = self.store
+        ops.check(self._L.mdt_forward(self._h, ops.ptr(st.w32), ops.ptr(st.w16), ops.ptr(x_in), ops.ptr(sigma),
+                                      ops.ptr(labels), ops.ptr(ids_keep), ops.ptr(ids_restore), B, T, int(save),
+                                      ops.ptr(ws), nbytes, ops.ptr(Fo), ops.stream_ptr()), "mdt_forward",
+                  self._count(save)[0])
+        ctx = None
+        if save:
+            ctx = dict(ws=ws, nbytes=nbytes, x_in=x_in, sigma=sigma, ids_keep=ids_keep, ids_restore=ids_restore, B=B,
+                       T=T)
+        return Fo, ctx
+
+    def backward(self, ctx, dF16, on_ready=None):
+        st = self.store
+        st.ensure_grad()
+        ops._c(dF16, bf16)
+        cb = ops.L.GRAD_READY_FN(lambda user, lo, hi: on_ready(lo, hi)) if on_ready is not None \
+            else ops.L.GRAD_READY_FN()
+        ops.check(self._L.mdt_backward(self._h, ops.ptr(st.w32), ops.ptr(st.w16), ops.ptr(st.grad), ops.ptr(ctx["x_in"]),
+                                       ops.ptr(ctx["sigma"]), ops.ptr(ctx["ids_keep"]), ops.ptr(ctx["ids_restore"]),
+                                       ops.ptr(dF16), ctx["B"], ctx["T"], ops.ptr(ctx["ws"]), ctx["nbytes"], cb, None,
+                                       ops.stream_ptr()), "mdt_backward", self._count(True)[1])
+
+
+def make_engine(cfg, store):
+    """MDT_ENGINE=py: kernel-by-kernel launches from Python (`Engine`); default: the C++ step driver (`CEngine`)."""
+    import os
+    return Engine(cfg, store) if os.environ.get("MDT_ENGINE", "c") == "py" else CEngine(cfg, store)

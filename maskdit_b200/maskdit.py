@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .engine import Engine
+from .engine import Engine, make_engine  # noqa: F401
 from .flat import FlatStore
 
 # (depth, hidden, heads) — models/maskdit.py:649-706
@@ -210,7 +210,7 @@ class EDMPrecond(nn.Module):
         st = self._store
         if not st.is_attached(params) or st.device != device:
             st.attach(params, device)
-            self._engine = Engine(self._cfg(), st)
+            self._engine = make_engine(self._cfg(), st)
             self._anchor = torch.zeros(1, device=device, requires_grad=True)
             self._graphs = {}
         if st.shadow_stale(params):
@@ -264,6 +264,8 @@ class EDMPrecond(nn.Module):
                 lab = torch.zeros(B, self.num_classes, device=x.device, dtype=torch.float32)
             else:
                 lab = class_labels.to(torch.float32).reshape(-1, self.num_classes).contiguous()
+                if lab.data_ptr() % 16:   # a row slice of a narrow label matrix: the vectorised kernels need 16 B
+                    lab = lab.clone()
         else:
             lab = None
         return xf, sig, lab

@@ -237,5 +237,6 @@ def to_uint8_nhwc(img):
 
 def adamw_ema(w, g, m, v, ema, w16, n, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
               ema_decay=0.9999, grad_scale=1.0, max_blocks=0):
-    check(lib().mdt_adamw_ema(ptr(w), ptr(g), ptr(m), ptr(v), ptr(ema), ptr(w16), n, lr, beta1, beta2, eps,
-                              weight_decay, step, ema_decay, grad_scale, max_blocks, stream_ptr()), "mdt_adamw_ema")
+    fn = lib().mdt_adamw_ema_g16 if g.dtype == bf16 else lib().mdt_adamw_ema   # bf16: all-reduced bf16 gradients
+    check(fn(ptr(w), ptr(g), ptr(m), ptr(v), ptr(ema), ptr(w16), n, lr, beta1, beta2, eps, weight_decay, step,
+             ema_decay, grad_scale, max_blocks, stream_ptr()), "mdt_adamw_ema")

@@ -2,14 +2,14 @@
 train_utils/helper.py:47-58 EMA).
 
 One process per GPU.  A step is:
-    zero flat grad  ->  fused EDM loss forward/backward (engine)  ->  NCCL all-reduce (SUM) of the flat fp32 gradient
-    buffer over NVLink (the 1/world factor is folded into the optimizer kernel)  ->  fused AdamW + EMA + bf16-shadow
-    kernel over the flat buffers.
-With `overlap=True` the flat buffer is reduced and stepped in per-block contiguous ranges on a side stream
-while the backward of the earlier blocks is still running (the role DDP's bucketed hooks play in the reference);
-with `overlap=False` (default: measured equal or faster up to 2 GPUs, see profiles/README.md) it is literally one
-all-reduce and one optimizer launch.  No other collective is issued in the
-step; the loss is returned as a device tensor (no per-step `.item()` host sync as at train.py:227).
+    zero flat grad  ->  fused EDM loss forward/backward (C++ step driver)  ->  sum-all-reduce of the flat gradient
+    buffer over NVLink (`GradComm`: our own NCCL communicator behind the C ABI; the 1/world factor is folded into the
+    optimizer kernel)  ->  fused AdamW + EMA + bf16-shadow kernel over the flat buffers.
+`overlap=False`: literally one all-reduce after the backward and one optimizer launch.  `overlap=True`: a block's
+gradient range is exchanged on a side stream as soon as its backward is enqueued (the role DDP's bucketed hooks play in
+the reference), through a communicator confined to a few CTAs while the persistent GEMM grids leave those SMs free
+(`mdt_set_sm_budget`), then one optimizer pass.  No other collective is issued in the step; the loss is
+returned as a device tensor (no per-step `.item()` host sync as at train.py:227).
 """
 from __future__ import annotations
 
@@ -70,11 +70,53 @@ def ar_chunk_bounds(n, k):
     return [(lo, min(n, lo + step)) for lo in range(0, n, step)]
 
 
+class GradComm:
+    """The step's gradient exchange behind the C ABI (`mdt_nccl_*`, `mdt_allreduce_grads`, csrc/driver.cu): an NCCL
+    communicator of our own, created from a unique id that rank 0 draws and `torch.distributed` merely ships to the
+    other ranks (any backend; it is the bootstrap side channel, nothing else).  `max_ctas` > 0 confines the
+    communicator's kernels to that many CTAs so that they run NEXT TO the backward instead of after it."""
+
+    def __init__(self, pg=None, max_ctas=0):
+        import ctypes
+        self.rank, self.world = dist.get_rank(pg), dist.get_world_size(pg)
+        L = ops.lib()
+        buf = ctypes.create_string_buffer(128)
+        if self.rank == 0:
+            ops.check(L.mdt_nccl_unique_id(buf), "mdt_nccl_unique_id", 0)
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(pg, 0) if pg is not None else 0, group=pg)
+        self._comm = ctypes.c_void_p()
+        ops.check(L.mdt_nccl_comm_create(box[0], self.rank, self.world, int(max_ctas), ctypes.byref(self._comm)),
+                  "mdt_nccl_comm_create", 0)
+        self.max_ctas = max_ctas
+
+    def all_reduce(self, t):
+        """In-place SUM over the ranks of a contiguous fp32 / bf16 device tensor, on the current stream."""
+        assert t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.bfloat16)
+        ops.check(ops.lib().mdt_allreduce_grads(self._comm, t.data_ptr(), t.numel(), int(t.dtype == torch.bfloat16),
+                                                ops.stream_ptr()), "mdt_allreduce_grads", 0)
+
+    def close(self):
+        if self._comm:
+            ops.lib().mdt_nccl_comm_destroy(self._comm)
+            self._comm = None
+
+
 class TrainStep:
     def __init__(self, net: EDMPrecond, ema: EDMPrecond | None = None, lr=1e-4, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=0.0, ema_decay=0.9999, loss_fn: EDMLoss | None = None, process_group=None,
                  lr_rampup_kimg=0.0, global_batch=None, device=None, overlap=False, graph=None,
-                 reference_lr_schedule=False):
+                 reference_lr_schedule=False, collective=None, grad_dtype=None, comm_ctas=None):
+        """Multi-GPU options (world > 1; SURVEY 8e: the step's ONLY collective is the sum of the flat gradient buffer):
+          collective  'mdt' (default with an NCCL process group): our own communicator behind the C ABI (`GradComm`);
+                      'torch': `torch.distributed.all_reduce` on the process group (gloo tests, A/B).
+          grad_dtype  'fp32' (default): the 2.92 GB fp32 buffer is reduced as is (DDP's arithmetic);
+                      'bf16': it is cast to a bf16 buffer first, 1.46 GB cross the links and the optimizer kernel reads
+                      bf16 gradients (moments and master weights stay fp32) - sanctioned by SURVEY 8e.
+          overlap     the exchange of a block's gradients starts as soon as its backward is enqueued, on a side stream,
+                      through a communicator confined to `comm_ctas` CTAs while the persistent GEMM / attention grids
+                      are sized for (SMs - comm_ctas) (`mdt_set_sm_budget`): the transfer hides behind the backward.
+        Environment overrides: MDT_COLLECTIVE, MDT_GRAD_AR, MDT_OVERLAP, MDT_COMM_CTAS."""
         self.net, self.ema = net, ema
         self.lr, self.betas, self.eps, self.wd, self.ema_decay = lr, betas, eps, weight_decay, ema_decay
         self.loss_fn = loss_fn or EDMLoss()
@@ -100,8 +142,22 @@ class TrainStep:
         for k, p in net.named_parameters():  # .grad views into the flat buffer (optimizer-compatible)
             if p.requires_grad:
                 p.grad = self.st.gview(k)
-        # Overlap: gradient ranges are reduced + stepped on a side stream as soon as a block's backward is enqueued.
-        self.overlap = overlap
+        # Overlap: gradient ranges are exchanged on a side stream as soon as a block's backward is enqueued.
+        env = os.environ
+        self.overlap = bool(int(env["MDT_OVERLAP"])) if "MDT_OVERLAP" in env else bool(overlap)
+        self.collective = env.get("MDT_COLLECTIVE") or collective or \
+            ("mdt" if self.world > 1 and dist.get_backend(process_group) == "nccl" else "torch")
+        self.grad_dtype = env.get("MDT_GRAD_AR") or grad_dtype or "fp32"
+        assert self.collective in ("mdt", "torch") and self.grad_dtype in ("fp32", "bf16")
+        self.comm_ctas = int(env.get("MDT_COMM_CTAS", comm_ctas if comm_ctas is not None else 8))
+        self.comm = None
+        self.g16 = None
+        if self.world > 1:
+            if self.collective == "mdt":
+                self.comm = GradComm(process_group, max_ctas=self.comm_ctas if self.overlap else 0)
+            if self.grad_dtype == "bf16":
+                self.g16 = torch.empty(n, dtype=torch.bfloat16, device=dev)
+        self._sms = torch.cuda.get_device_properties(dev).multi_processor_count
         self.graph = (os.environ.get("MDT_TRAIN_GRAPH", "0") == "1") if graph is None else bool(graph)
         self._graphs = {}
         self.bg_blocks = 24
@@ -109,10 +165,10 @@ class TrainStep:
         # flat call: measured on 2 x B200 (same box) 132.0 ms/step flat vs 133.3 ms with 8 chunks - the all-reduce and
         # the AdamW/EMA pass are both HBM-bound, so running them side by side buys nothing.
         self.ar_chunks = int(os.environ.get("MDT_AR_CHUNKS", "1"))
-        self.side = torch.cuda.Stream(device=dev) if overlap else None
+        self.side = torch.cuda.Stream(device=dev, priority=-1) if self.overlap else None
         self._done = []          # [lo, hi) ranges already handled in the current step
         self._lr_now = lr
-        net._grad_ready_hook = self._on_grads_ready if overlap else None
+        net._grad_ready_hook = self._on_grads_ready if (self.overlap and self.world > 1) else None
 
     # -- optimizer state for checkpoints (reference: train.py:259-270 stores optimizer.state_dict() under 'opt') ------
     def state_dict(self):
@@ -171,32 +227,47 @@ class TrainStep:
         self.lr, self.betas, self.eps, self.wd = group["lr"], tuple(group["betas"]), group["eps"], \
             group["weight_decay"]
 
-    # -- one gradient range: (all-reduce) + fused AdamW/EMA/bf16-shadow, on the current stream -----------------------
-    def _reduce_and_step(self, lo, hi, max_blocks=0):
-        st, n = self.st, hi - lo
-        if n <= 0:
+    # -- gradient exchange + optimizer ------------------------------------------------------------------------------------
+    def describe_collective(self):
+        if self.world == 1:
+            return "none (1 GPU)"
+        how = "own NCCL communicator behind the C ABI (mdt_allreduce_grads)" if self.comm else "torch.distributed"
+        when = (f"per block during the backward on a side stream ({self.comm_ctas} comm CTAs, persistent grids sized "
+                f"for {self._sms - self.comm_ctas} SMs)") if self.overlap else "one flat call after the backward"
+        return f"{self.grad_dtype} sum-all-reduce of the flat gradient buffer, {how}, {when}"
+
+    def _exchange(self, lo, hi):
+        """Sum gradient elements [lo, hi) over the ranks on the current stream (in `grad`, or in the bf16 buffer)."""
+        if hi <= lo or self.world == 1:
             return
-        if self.world > 1:
-            dist.all_reduce(st.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
-        self._step_range(lo, hi, max_blocks)
+        st = self.st
+        buf = st.grad[lo:hi]
+        if self.g16 is not None:
+            buf = ops.cast_bf16(buf, out=self.g16[lo:hi])
+        if self.comm is not None:
+            self.comm.all_reduce(buf)
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)
 
     def _step_range(self, lo, hi, max_blocks=0):
         st, n = self.st, hi - lo
         if n <= 0:
             return
-        g = st.grad[lo:hi]
+        g = self.g16[lo:hi] if (self.g16 is not None and self.world > 1) else st.grad[lo:hi]
         ops.adamw_ema(st.w32[lo:hi], g, self.m[lo:hi], self.v[lo:hi],
                       self.ema_st.w32[lo:hi] if self.ema_st is not None else None, st.w16[lo:hi], n, self._lr_now,
                       self.step_count, self.betas[0], self.betas[1], self.eps, self.wd, self.ema_decay,
                       self._grad_scale, max_blocks)
 
     def _on_grads_ready(self, lo, hi):
+        """Called (on the host, from inside mdt_backward) when the kernels finalising gradient elements [lo, hi) of one
+        block are enqueued: start their exchange behind them on the side stream."""
+        if not self._done:   # first block of this backward: from here on the persistent grids leave SMs to the collective
+            ops.check(ops.lib().mdt_set_sm_budget(self._sms - self.comm_ctas), "mdt_set_sm_budget", 0)
         main = torch.cuda.current_stream()
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
-            # background launch: a block's optimizer pass needs <2 % of the HBM bandwidth to finish before the backward
-            # does, so it is capped to a few CTAs and leaves the SMs to the tensor-core GEMMs
-            self._reduce_and_step(lo, hi, max_blocks=self.bg_blocks)
+            self._exchange(lo, hi)
         self._done.append((lo, hi))
 
     def _fwd_bwd_graphed(self, images, labels, mask_ratio, mae_loss_coef, loss_call, moments=False):
@@ -294,26 +365,37 @@ class TrainStep:
             loss = loss_call(self.net, images, labels, mask_ratio, mae_loss_coef)
             loss.mean().backward()   # engine backward; with overlap=True block ranges are already being reduced/stepped
         main = torch.cuda.current_stream()
-        if self.overlap:
+        if self.world == 1:
+            self._step_range(0, st.n_train)
+        elif self.overlap:
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side):
                 cur = 0
                 for lo, hi in sorted(self._done) + [(st.n_train, st.n_train)]:   # the complement of the block ranges
-                    self._reduce_and_step(cur, lo)
+                    self._exchange(cur, lo)
                     cur = max(cur, hi)
+            ops.check(ops.lib().mdt_set_sm_budget(0), "mdt_set_sm_budget", 0)
             main.wait_stream(self.side)
-        elif self.world > 1 and self.ar_chunks > 1:
-            # The all-reduce is exposed after the backward (overlapping it with the persistent GEMMs costs more than
-            # it hides), but it need not also serialise with the optimizer: the flat gradient is reduced in chunks on
-            # NCCL's stream and the fused AdamW/EMA pass of chunk k runs while chunk k+1 is still on the wire.
+            self._step_range(0, st.n_train)          # ONE optimizer pass over the whole (reduced) buffer
+        elif self.ar_chunks > 1:
+            # pipeline the exposed all-reduce against the optimizer pass: chunk k is stepped while k+1 is on the wire
+            if self.side is None:
+                self.side = torch.cuda.Stream(device=st.grad.device)
             bounds = ar_chunk_bounds(st.n_train, self.ar_chunks)
-            works = [dist.all_reduce(st.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
-                     for lo, hi in bounds]
-            for (lo, hi), w in zip(bounds, works):
-                w.wait()   # the current stream waits for this chunk only
+            self.side.wait_stream(main)
+            evs = []
+            with torch.cuda.stream(self.side):
+                for lo, hi in bounds:
+                    self._exchange(lo, hi)
+                    ev = torch.cuda.Event()
+                    ev.record(self.side)
+                    evs.append(ev)
+            for (lo, hi), ev in zip(bounds, evs):
+                main.wait_event(ev)
                 self._step_range(lo, hi)
         else:
-            self._reduce_and_step(0, st.n_train)   # one flat all-reduce + one optimizer pass
+            self._exchange(0, st.n_train)            # one flat all-reduce ...
+            self._step_range(0, st.n_train)          # ... + one optimizer pass
         st.mark_shadow_fresh(self.net._params())   # the kernel refreshed the bf16 shadow itself
         if self.ema_st is not None:
             self.ema_st._versions = None           # EMA weights changed behind PyTorch's back: shadow is stale

@@ -200,3 +200,46 @@ def test_config_schema_and_mask_schedule():
     with pytest.raises(ValueError):
         mask_ratio_schedule("bogus")
     assert parse_int_list("1,2,5-8") == [1, 2, 5, 6, 7, 8] and parse_float_none("None") is None
+
+
+@pytest.mark.parametrize("mt,R,ncls", [("DiT-S/2", 8, 10), ("DiT-B/4", 16, 7), ("DiT-XL/2", 32, 1000), ("DiT-XL/2", 64, 1000)])
+def test_c_driver_layout_equals_flat_store(mt, R, ncls):
+    """The packed parameter blob `mdt_model_param_info` enumerates (csrc/driver.cu) is exactly the layout FlatStore
+    builds for the nn.Module — names = the reference's state-dict keys — and the workspace planner is monotone."""
+    import ctypes
+    from maskdit_b200 import _lib
+    from maskdit_b200.flat import FlatStore
+    from oracle import maskdit_oracle as O
+    from maskdit_b200.maskdit import Precond_models
+    cfg = O.Cfg(model_type=mt, img_resolution=R, num_classes=ncls)
+    with torch.device("meta"):   # registration order of the module (= the reference's, see make_golden.py's strict load)
+        net = Precond_models["edm"](R, 4, num_classes=ncls, model_type=mt, use_decoder=True, mae_loss_coef=0.1)
+    shapes = {k: tuple(p.shape) for k, p in net.named_parameters()}
+    assert shapes == {k: tuple(v) for k, v in O.param_shapes(cfg).items()}
+    st = FlatStore()
+    st.plan(shapes)
+    L = _lib.lib()
+    mc = _lib.ModelCfg(R, 4, cfg.patch, ncls, cfg.hidden, cfg.depth, cfg.heads, 4 * cfg.hidden, 512, 8, 16, 2048, 1, 0.5)
+    h = ctypes.c_void_p()
+    assert L.mdt_model_create(ctypes.byref(mc), ctypes.byref(h)) == 0
+    n = L.mdt_model_num_tensors(h)
+    assert n == len(shapes)
+    name, off, num = ctypes.create_string_buffer(160), ctypes.c_longlong(), ctypes.c_longlong()
+    prev = -1
+    for i in range(n):
+        assert L.mdt_model_param_info(h, i, name, 160, ctypes.byref(off), ctypes.byref(num)) == 0
+        k = name.value.decode()
+        assert st.offsets[k][:2] == (off.value, num.value), k
+        assert off.value > prev and off.value % 64 == 0
+        prev = off.value
+    assert L.mdt_model_param_info(h, n, name, 160, None, None) != 0
+    assert (L.mdt_model_param_count(h, 1), L.mdt_model_param_count(h, 0)) == (st.n_train, st.n_total)
+    if mt == "DiT-XL/2":
+        assert L.mdt_model_param_count(h, 1) >= 730_115_216
+    T = cfg.num_patches // 2
+    tr, ev = L.mdt_workspace_bytes(h, 8, T, 1), L.mdt_workspace_bytes(h, 8, 0, 0)
+    assert tr > ev > 0 and L.mdt_workspace_bytes(h, 16, T, 1) > tr and L.mdt_workspace_bytes(h, 0, T, 1) < 0
+    bad = _lib.ModelCfg(R, 4, cfg.patch, ncls, cfg.hidden + 1, cfg.depth, cfg.heads, 4 * cfg.hidden, 512, 8, 16, 2048, 1, 0.5)
+    h2 = ctypes.c_void_p()
+    assert L.mdt_model_create(ctypes.byref(bad), ctypes.byref(h2)) != 0     # hidden not divisible by heads
+    L.mdt_model_destroy(h)

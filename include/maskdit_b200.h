@@ -68,6 +68,8 @@ typedef struct mdt_gemm_args {
   int ld_gate;
   int rows_per_group;
   int block_n;   /* 0 = auto, or 128/192/256 */
+  float* colsum; /* MDT_EPI_DGELU only, may be NULL: colsum[n] += sum_m out[m,n] (the bf16-rounded outputs), i.e. the
+                    bias gradient of the layer whose pre-activation gradient this GEMM produces (fp32 red.add)      */
 } mdt_gemm_args;
 
 int mdt_gemm_bf16(const mdt_gemm_args* args, void* stream);

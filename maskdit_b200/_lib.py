@@ -33,6 +33,7 @@ class GemmArgs(Structure):
         ("gate", c_void_p), ("ld_gate", c_int),
         ("rows_per_group", c_int),
         ("block_n", c_int),
+        ("colsum", c_void_p),
     ]
 
 
@@ -165,7 +166,7 @@ def _req_cuda(*ts):
 
 def gemm(A, B, M, N, K, *, lda=None, ldb=None, a_mn=False, b_mn=False, epi=EPI_STORE, act=ACT_NONE, out=None,
          ldo=None, bias=None, aux=None, ld_aux=0, resid=None, ld_resid=0, gate=None, ld_gate=0, rows_per_group=1,
-         block_n=0):
+         block_n=0, colsum=None):
     """out[M,N] (+)= sum_k A[m,k] B[n,k].  `out` dtype (bf16/fp32) selects the store type."""
     _req_cuda(A, B, out)
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
@@ -184,6 +185,7 @@ def gemm(A, B, M, N, K, *, lda=None, ldb=None, a_mn=False, b_mn=False, epi=EPI_S
     a.gate, a.ld_gate = ptr(gate), ld_gate
     a.rows_per_group = rows_per_group
     a.block_n = block_n
+    a.colsum = ptr(colsum)
     if GEMM_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -20,7 +20,7 @@ const char* mdt_status_string(int status) {
   }
 }
 
-int mdt_abi_version(void) { return 1; }
+int mdt_abi_version(void) { return 2; }  // 2: mdt_gemm_args.colsum, step driver, gradient exchange
 
 int mdt_set_sm_budget(int n) {
   if (n < 0) return MDT_ERR_ARG;

@@ -286,6 +286,7 @@ struct Gemm {
   Gemm& epi(int e) { a.epi = e; return *this; }
   Gemm& aux(void* x, int ld) { a.aux = x, a.ld_aux = ld; return *this; }
   Gemm& resid(const float* r, int ld) { a.resid = r, a.ld_resid = ld; return *this; }
+  Gemm& colsum(float* cs) { a.colsum = cs; return *this; }
   Gemm& gate(const float* g, int ld, int rpg) { a.gate = g, a.ld_gate = ld, a.rows_per_group = rpg; return *this; }
   void run(Ctx& c) { if (c.rc == MDT_OK) c.ck(mdt_gemm_bf16(&a, c.stream)); }
 };
@@ -367,9 +368,10 @@ void block_bwd(Ctx& c, const Plan& p, const BlockP& s, const BlockBuf& b, const 
   const i64 M = static_cast<i64>(B) * T, o = s.mod_off;
   void* st = c.stream;
   __nv_bfloat16* dh = c.at<__nv_bfloat16>(p.dh);
-  Gemm(dy2, c.W16(s.fc2_w), M, h4, d, false, true).out16(dh).epi(MDT_EPI_DGELU).aux(c.at<void>(b.hpre), h4).run(c);
+  // (the fc1 bias gradient = column sums of dh is accumulated by the epilogue that writes dh: no separate pass)
+  Gemm(dy2, c.W16(s.fc2_w), M, h4, d, false, true).out16(dh).epi(MDT_EPI_DGELU).aux(c.at<void>(b.hpre), h4)
+      .colsum(c.Gd(s.fc1_b)).run(c);
   wgrad(c, dy2, c.at<void>(b.a), d, h4, M, c.Gd(s.fc2_w));
-  c.ck(mdt_colsum_bf16(dh, static_cast<int>(M), h4, h4, c.Gd(s.fc1_b), st));
   __nv_bfloat16* dxm = c.at<__nv_bfloat16>(p.dxm);
   Gemm(dh, c.W16(s.fc1_w), M, d, h4, false, true).out16(dxm).run(c);
   wgrad(c, dh, c.at<void>(b.xm2), h4, d, M, c.Gd(s.fc1_w));

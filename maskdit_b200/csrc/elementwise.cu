@@ -38,7 +38,8 @@ __global__ void mask_indices_kernel(const float* __restrict__ noise, int L, int 
 // =========================================================================================================
 // PatchEmbed (+c_in, +pos_embed, +kept-token gather).  Block = 8 tokens of one sample, threads over D.
 // =========================================================================================================
-constexpr int kPeTok = 8;
+constexpr int kPeTok = 32;   // tokens per block: the weight row of a channel (C*p*p floats) is read once per 32 tokens
+constexpr int kPeMaxCpp = 64;
 __global__ void patch_embed_kernel(const float* __restrict__ x, const float* __restrict__ sigma, float sigma_data,
                                    const float* __restrict__ W, const float* __restrict__ bias,
                                    const float* __restrict__ pos, const int64_t* __restrict__ ids_keep,
@@ -62,28 +63,40 @@ __global__ void patch_embed_kernel(const float* __restrict__ x, const float* __r
     s_patch[e] = v;
   }
   __syncthreads();
+  const int nt = min(kPeTok, T - i0);
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     const float* w = W + static_cast<size_t>(d) * cpp;
     const float bd = bias[d];
-    float acc[kPeTok];
+    if (cpp == 16) {  // patch 2 x 4 channels (every shipped config): the weight row lives in registers
+      float wr[16];
 #pragma unroll
-    for (int t = 0; t < kPeTok; ++t) acc[t] = bd;
-    for (int j = 0; j < cpp; ++j) {
-      const float wj = __ldg(w + j);
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(w) + q);
+        wr[4 * q] = v.x, wr[4 * q + 1] = v.y, wr[4 * q + 2] = v.z, wr[4 * q + 3] = v.w;
+      }
+      for (int t = 0; t < nt; ++t) {
+        float acc = bd;
+        const float4* sp = reinterpret_cast<const float4*>(s_patch + t * 16);  // smem broadcast reads
 #pragma unroll
-      for (int t = 0; t < kPeTok; ++t) acc[t] = fmaf(wj, s_patch[t * cpp + j], acc[t]);
-    }
-#pragma unroll
-    for (int t = 0; t < kPeTok; ++t) {
-      const int i = i0 + t;
-      if (i < T)
-        out[(static_cast<size_t>(b) * T + i) * D + d] = acc[t] + pos[static_cast<size_t>(s_tok[t]) * D + d];
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = sp[q];
+          acc = fmaf(wr[4 * q], v.x, acc), acc = fmaf(wr[4 * q + 1], v.y, acc);
+          acc = fmaf(wr[4 * q + 2], v.z, acc), acc = fmaf(wr[4 * q + 3], v.w, acc);
+        }
+        out[(static_cast<size_t>(b) * T + i0 + t) * D + d] = acc + pos[static_cast<size_t>(s_tok[t]) * D + d];
+      }
+    } else {
+      for (int t = 0; t < nt; ++t) {
+        float acc = bd;
+        for (int j = 0; j < cpp; ++j) acc = fmaf(__ldg(w + j), s_patch[t * cpp + j], acc);
+        out[(static_cast<size_t>(b) * T + i0 + t) * D + d] = acc + pos[static_cast<size_t>(s_tok[t]) * D + d];
+      }
     }
   }
 }
 
 // gW[d, j] += sum_tokens g[tok, d] * patch[tok, j]; gb[d] += sum g.  Block = 64 tokens of one sample.
-constexpr int kPebTok = 64;
+constexpr int kPebTok = 128;  // tokens per block (one atomic per (channel, weight) per block)
 __global__ void patch_embed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ sigma,
                                        float sigma_data, const int64_t* __restrict__ ids_keep,
                                        const float* __restrict__ g, float* __restrict__ gW, float* __restrict__ gb,

@@ -24,6 +24,7 @@ struct GemmParams {
   int ld_resid;
   const float* gate;
   int ld_gate, rows_per_group;
+  float* colsum;
 };
 
 int gemm_launch(const mdt_gemm_args& a, cudaStream_t stream);

@@ -159,7 +159,8 @@ MDT_DEVINL void epi_load(const GemmParams& p, const EpiCoord& c, int lane, EpiOp
 
 // chunk `c` (valid for this lane): transpose-read, fused arithmetic, coalesced stores
 template <int EPI>
-MDT_DEVINL void epilogue_chunk(const GemmParams& p, uint32_t stg, const EpiCoord& c, int lane, const EpiOps<EPI>& o) {
+MDT_DEVINL void epilogue_chunk(const GemmParams& p, uint32_t stg, const EpiCoord& c, int lane, const EpiOps<EPI>& o,
+                               float4& cs_out) {
   const int rsub = lane >> 3, c4 = (lane & 7) * 4;
   const float4 bias4 = o.bias4;
   const size_t row0 = static_cast<size_t>(c.row_base + rsub);
@@ -168,6 +169,7 @@ MDT_DEVINL void epilogue_chunk(const GemmParams& p, uint32_t stg, const EpiCoord
   const uint64_t a_aux = gaddr(p.aux) + (row0 * p.ld_aux + c.col) * 2;
   const uint64_t s_out = 4ull * p.ldo * osz, s_aux = 8ull * p.ld_aux;
   const uint32_t sp = stg + (rsub * kStgStride + c4) * 4;
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);  // EPI_DGELU: column sums of this lane's outputs (bias gradient)
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     if (4 * i + rsub >= c.nrows) break;
@@ -198,11 +200,15 @@ MDT_DEVINL void epilogue_chunk(const GemmParams& p, uint32_t stg, const EpiCoord
         stg128(ao, make_float4(fmaf(g.x, v.x, r.x), fmaf(g.y, v.y, r.y), fmaf(g.z, v.z, r.z), fmaf(g.w, v.w, r.w)));
       } else if constexpr (EPI == EPI_DGELU) {
         const float4 h = unpack4_bf16(o.auxv[i]);
-        stg64(ao, pack4_bf16(make_float4(v.x * gelu_tanh_grad(h.x), v.y * gelu_tanh_grad(h.y),
-                                         v.z * gelu_tanh_grad(h.z), v.w * gelu_tanh_grad(h.w))));
+        const uint2 ov = pack4_bf16(make_float4(v.x * gelu_tanh_grad(h.x), v.y * gelu_tanh_grad(h.y),
+                                                v.z * gelu_tanh_grad(h.z), v.w * gelu_tanh_grad(h.w)));
+        stg64(ao, ov);
+        const float4 r = unpack4_bf16(ov);  // sum what was stored (what a separate column-sum pass would read back)
+        cs.x += r.x, cs.y += r.y, cs.z += r.z, cs.w += r.w;
       }
     }
   }
+  if constexpr (EPI == EPI_DGELU) cs_out = cs;
 }
 
 // ragged right edge (N % 4 != 0 inside this 4-column group): element-wise, same arithmetic, cold path
@@ -239,7 +245,11 @@ __device__ __noinline__ void epilogue_ragged(const GemmParams& p, uint32_t stg, 
           if (p.aux) *aux = __float2bfloat16_rn(v);
           *o32 = fmaf(p.gate[(row / p.rows_per_group) * p.ld_gate + c], v, p.resid[row * p.ld_resid + c]);
           break;
-        case EPI_DGELU: *o16 = __float2bfloat16_rn(v * gelu_tanh_grad(__bfloat162float(*aux))); break;
+        case EPI_DGELU: {
+          const __nv_bfloat16 r = __float2bfloat16_rn(v * gelu_tanh_grad(__bfloat162float(*aux)));
+          *o16 = r;
+          if (p.colsum) atomicAdd(p.colsum + c, __bfloat162float(r));
+        } break;
         default: break;
       }
     }
@@ -305,8 +315,19 @@ MDT_DEVINL void epilogue_loop(const GemmParams& p, UnitSched& sched, uint64_t* t
         __syncwarp();
         MDT_GPROF(2)  // staging stores
         if constexpr (kHasOps || EPI == EPI_ATOMIC) {
-          if (c.valid) epilogue_chunk<EPI>(p, stg, c, lane, ops);
+          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c.valid) epilogue_chunk<EPI>(p, stg, c, lane, ops, cs);
           else if (c.col < p.N) epilogue_ragged(p, stg, row_base, nrows, c.col, lane);
+          if constexpr (EPI == EPI_DGELU) {
+            if (p.colsum) {  // launch-uniform: bias gradient = column sums of the stored tile (fused colsum pass)
+              __syncwarp();  // lanes l, l^8, l^16, l^24 own the same 4 columns (different row groups)
+              cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8), cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
+              cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8), cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
+              cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16), cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+              cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16), cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+              if (lane < 8 && c.valid) red_add_v4(gaddr(p.colsum + c.col), cs);
+            }
+          }
         }
         __syncwarp();
         MDT_GPROF(3)  // transposed read, fused math, global stores
@@ -618,6 +639,7 @@ static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
   p.aux = a.aux, p.ld_aux = a.ld_aux;
   p.resid = a.resid, p.ld_resid = a.ld_resid;
   p.gate = a.gate, p.ld_gate = a.ld_gate, p.rows_per_group = a.rows_per_group > 0 ? a.rows_per_group : 1;
+  p.colsum = a.epi == EPI_DGELU ? a.colsum : nullptr;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int groups = num_sms() / CG;  // CTA groups resident at once (1 CTA per SM)
   // k-slices: only for the accumulate epilogue (fp32 red.add).  Pick the smallest slice count whose unit count

@@ -284,11 +284,11 @@ class Engine:
             dy2 = ops.gate_bwd(Gr, sv["y2"], mod[:, o + 5 * D:], NA, T, dmod[:, o + 5 * D:], NA,
                                G(f"{p}.mlp.fc2.bias"), M, D)
         dh = torch.empty(M, H4, dtype=bf16, device=dev)
+        # the fc1 bias gradient (column sums of dh) is accumulated by the same epilogue that writes dh
         gemm(dy2, self.w16(f"{p}.mlp.fc2.weight"), M, H4, D, b_mn=True, out=dh, epi=EPI_DGELU, aux=sv["hpre"],
-             ld_aux=H4)
+             ld_aux=H4, colsum=G(f"{p}.mlp.fc1.bias"))
         self._wgrad(dy2, sv["a"], D, H4, M, G(f"{p}.mlp.fc2.weight"))
         del dy2
-        ops.colsum(dh, G(f"{p}.mlp.fc1.bias"))
         dxm2 = torch.empty(M, D, dtype=bf16, device=dev)
         gemm(dh, self.w16(f"{p}.mlp.fc1.weight"), M, D, H4, b_mn=True, out=dxm2)
         self._wgrad(dh, sv["xm2"], H4, D, M, G(f"{p}.mlp.fc1.weight"))
@@ -364,7 +364,7 @@ class CEngine:
         c = self.cfg
         nb = c.depth + c.dec_depth
         fwd = 12 + (2 if c.num_classes else 0) + 7 * nb          # embed/conditioning 7, decoder layer 3, final 2
-        bwd = 21 + 14 * nb + (1 if c.num_classes else 0)         # final 4, transition 5, patch-embed 1, conditioning 11
+        bwd = 21 + 13 * nb + (1 if c.num_classes else 0)         # final 4, transition 5, patch-embed 1, conditioning 11
         return fwd, bwd
 
     def forward(self, x_in, sigma, labels, mask_dict, save):

@@ -154,13 +154,12 @@ class TrainStep:
         self.g16 = None
         if self.world > 1:
             if self.collective == "mdt":
-                self.comm = GradComm(process_group, max_ctas=self.comm_ctas if self.overlap else 0)
+                self.comm = GradComm(process_group, max_ctas=max(1, self.comm_ctas // 2) if self.overlap else 0)
             if self.grad_dtype == "bf16":
                 self.g16 = torch.empty(n, dtype=torch.bfloat16, device=dev)
         self._sms = torch.cuda.get_device_properties(dev).multi_processor_count
         self.graph = (os.environ.get("MDT_TRAIN_GRAPH", "0") == "1") if graph is None else bool(graph)
         self._graphs = {}
-        self.bg_blocks = 24
         # gradient all-reduce in this many chunks, pipelined against the optimizer pass (world > 1).  Default 1 = one
         # flat call: measured on 2 x B200 (same box) 132.0 ms/step flat vs 133.3 ms with 8 chunks - the all-reduce and
         # the AdamW/EMA pass are both HBM-bound, so running them side by side buys nothing.
@@ -168,7 +167,11 @@ class TrainStep:
         self.side = torch.cuda.Stream(device=dev, priority=-1) if self.overlap else None
         self._done = []          # [lo, hi) ranges already handled in the current step
         self._lr_now = lr
-        net._grad_ready_hook = self._on_grads_ready if (self.overlap and self.world > 1) else None
+        # background optimizer: with overlap, a block's AdamW+EMA pass also runs on the side stream right after its
+        # exchange (HBM-bound work next to the tensor-bound backward, on the SMs the budget leaves free)
+        self.bg_opt = self.overlap and env.get("MDT_BG_OPT", "1") == "1"
+        self.bg_blocks = int(env.get("MDT_BG_BLOCKS", 8 * max(1, self.comm_ctas)))
+        net._grad_ready_hook = self._on_grads_ready if self.overlap else None
 
     # -- optimizer state for checkpoints (reference: train.py:259-270 stores optimizer.state_dict() under 'opt') ------
     def state_dict(self):
@@ -262,12 +265,14 @@ class TrainStep:
     def _on_grads_ready(self, lo, hi):
         """Called (on the host, from inside mdt_backward) when the kernels finalising gradient elements [lo, hi) of one
         block are enqueued: start their exchange behind them on the side stream."""
-        if not self._done:   # first block of this backward: from here on the persistent grids leave SMs to the collective
+        if not self._done:   # first block of this backward: from here on the persistent grids leave SMs to the side stream
             ops.check(ops.lib().mdt_set_sm_budget(self._sms - self.comm_ctas), "mdt_set_sm_budget", 0)
         main = torch.cuda.current_stream()
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
             self._exchange(lo, hi)
+            if self.bg_opt:
+                self._step_range(lo, hi, max_blocks=self.bg_blocks)
         self._done.append((lo, hi))
 
     def _fwd_bwd_graphed(self, images, labels, mask_ratio, mae_loss_coef, loss_call, moments=False):
@@ -365,18 +370,21 @@ class TrainStep:
             loss = loss_call(self.net, images, labels, mask_ratio, mae_loss_coef)
             loss.mean().backward()   # engine backward; with overlap=True block ranges are already being reduced/stepped
         main = torch.cuda.current_stream()
-        if self.world == 1:
-            self._step_range(0, st.n_train)
-        elif self.overlap:
+        if self.overlap and self._done:
+            ops.check(ops.lib().mdt_set_sm_budget(0), "mdt_set_sm_budget", 0)
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side):
                 cur = 0
                 for lo, hi in sorted(self._done) + [(st.n_train, st.n_train)]:   # the complement of the block ranges
                     self._exchange(cur, lo)
+                    if self.bg_opt:
+                        self._step_range(cur, lo)
                     cur = max(cur, hi)
-            ops.check(ops.lib().mdt_set_sm_budget(0), "mdt_set_sm_budget", 0)
             main.wait_stream(self.side)
-            self._step_range(0, st.n_train)          # ONE optimizer pass over the whole (reduced) buffer
+            if not self.bg_opt:
+                self._step_range(0, st.n_train)      # ONE optimizer pass over the whole (reduced) buffer
+        elif self.world == 1:
+            self._step_range(0, st.n_train)
         elif self.ar_chunks > 1:
             # pipeline the exposed all-reduce against the optimizer pass: chunk k is stepped while k+1 is on the wire
             if self.side is None:

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
-    assert _lib.lib().mdt_abi_version() == 1
+    assert _lib.lib().mdt_abi_version() == 2
     assert _lib.lib().mdt_status_string(-1).decode().startswith("invalid argument")
 
 

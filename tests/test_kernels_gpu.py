@@ -91,6 +91,13 @@ def test_gemm_epilogues(ops):
     hf = h.float().requires_grad_(True)
     F.gelu(hf, approximate="tanh").sum().backward()
     close(o16, (A.float() @ B.float().t()) * hf.grad, 2 ** -7, "dgelu")
+    # fused bias gradient: colsum[n] += sum_m of the STORED (bf16-rounded) outputs, incl. a ragged N (1000) and odd M
+    for (m2, n2) in ((M, N), (300, 1000)):
+        A2, B2, h2 = rb(m2, K), rb(n2, K, scale=0.05), rb(m2, n2)
+        o2 = torch.empty(m2, n2, device=dev(), dtype=torch.bfloat16)
+        cs = torch.full((n2,), 0.5, device=dev())
+        ops.gemm(A2, B2, m2, n2, K, out=o2, epi=ops.EPI_DGELU, aux=h2, ld_aux=n2, colsum=cs)
+        close(cs - 0.5, o2.float().sum(0), 1e-4, f"dgelu colsum {m2}x{n2}")
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -76,9 +76,9 @@ def main():
         return ((a.double() - b.double()).norm() / b.double().norm()).item()
 
     results = {}
-    for name, kw, tol in (("mdt fp32 flat", dict(collective="mdt", grad_dtype="fp32", overlap=False), 1e-5),
-                          ("torch fp32 flat", dict(collective="torch", grad_dtype="fp32", overlap=False), 1e-5),
-                          ("mdt fp32 overlapped", dict(collective="mdt", grad_dtype="fp32", overlap=True), 1e-5),
+    for name, kw, tol in (("mdt fp32 flat", dict(collective="mdt", grad_dtype="fp32", overlap=False), 5e-5),
+                          ("torch fp32 flat", dict(collective="torch", grad_dtype="fp32", overlap=False), 5e-5),
+                          ("mdt fp32 overlapped", dict(collective="mdt", grad_dtype="fp32", overlap=True), 5e-5),
                           ("mdt bf16 flat", dict(collective="mdt", grad_dtype="bf16", overlap=False), 6e-3),
                           ("mdt bf16 overlapped", dict(collective="mdt", grad_dtype="bf16", overlap=True), 6e-3)):
         gm, w, ts = run(**kw)

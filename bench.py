@@ -338,6 +338,7 @@ def bench_train(args, net, env, R, PK, B, steps, warmup, full):
                "config": {"workload": workload, "batch_per_gpu": B, "global_batch": B * world},
                "roofline": {"bound": "tensor", "step_achieved": step_tf, "peak": PK["sustained"], "unit": "TFLOP/s",
                             "step_frac": step_tf / PK["sustained"], "peak_source": f"{PK['src']} sustained bf16"}}
+        ts.close()
         del ts, ema, resident
         torch.cuda.empty_cache()
         return rec
@@ -379,6 +380,7 @@ def bench_train(args, net, env, R, PK, B, steps, warmup, full):
                      "launches_per_step": len(prof), "share_of_step": gemm_ms / ms_step,
                      "step_achieved": step_tf, "step_frac": step_tf / PK["sustained"]},
     }
+    ts.close()
     del ts, ema, resident
     torch.cuda.empty_cache()
     return line

@@ -503,20 +503,33 @@ ln_bwd_gate_kernel(const __nv_bfloat16* __restrict__ dxmod, const float* __restr
 // =========================================================================================================
 // unmask_tokens (+ decoder_pos_embed) and its backward.  Thread owns 4 columns; block = D/4 threads x 16 positions.
 // =========================================================================================================
-constexpr int kUmPos = 16;
+constexpr int kUmPos = 64;  // positions per block (backward: one 16-byte mask-token reduction per thread and block)
 __global__ void unmask_kernel(const float* __restrict__ u, const float* __restrict__ mask_token,
                               const float* __restrict__ pos, const int64_t* __restrict__ ids_restore,
                               float* __restrict__ out, int T, int L, int D) {
   const int c = threadIdx.x * 4;
   if (c >= D) return;
-  const int b = blockIdx.y, l0 = blockIdx.x * kUmPos;
+  const int b = blockIdx.y, l0 = blockIdx.x * kUmPos, l1 = min(L, l0 + kUmPos);
   const float4 mt = mask_token ? *reinterpret_cast<const float4*>(mask_token + c) : make_float4(0, 0, 0, 0);
-  for (int l = l0; l < min(L, l0 + kUmPos); ++l) {
-    const int r = ids_restore ? static_cast<int>(ids_restore[static_cast<size_t>(b) * L + l]) : l;
-    float4 v = (r < T) ? *reinterpret_cast<const float4*>(u + (static_cast<size_t>(b) * T + r) * D + c) : mt;
-    const float4 pe = *reinterpret_cast<const float4*>(pos + static_cast<size_t>(l) * D + c);
-    v.x += pe.x, v.y += pe.y, v.z += pe.z, v.w += pe.w;
-    *reinterpret_cast<float4*>(out + (static_cast<size_t>(b) * L + l) * D + c) = v;
+  // 4 positions per iteration: the index loads, then the 8 independent 16-byte row loads, are issued back to back
+  for (int l = l0; l < l1; l += 4) {
+    int r[4];
+    float4 v[4], pe[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      r[j] = (l + j < l1) ? (ids_restore ? static_cast<int>(ids_restore[static_cast<size_t>(b) * L + l + j]) : l + j) : -1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (r[j] < 0) continue;
+      v[j] = (r[j] < T) ? *reinterpret_cast<const float4*>(u + (static_cast<size_t>(b) * T + r[j]) * D + c) : mt;
+      pe[j] = *reinterpret_cast<const float4*>(pos + static_cast<size_t>(l + j) * D + c);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (r[j] < 0) continue;
+      *reinterpret_cast<float4*>(out + (static_cast<size_t>(b) * L + l + j) * D + c) =
+          make_float4(v[j].x + pe[j].x, v[j].y + pe[j].y, v[j].z + pe[j].z, v[j].w + pe[j].w);
+    }
   }
 }
 __global__ void unmask_bwd_kernel(const float* __restrict__ g, const int64_t* __restrict__ ids_restore,
@@ -524,21 +537,32 @@ __global__ void unmask_bwd_kernel(const float* __restrict__ g, const int64_t* __
                                   int D) {
   const int c = threadIdx.x * 4;
   if (c >= D) return;
-  const int b = blockIdx.y, l0 = blockIdx.x * kUmPos;
+  const int b = blockIdx.y, l0 = blockIdx.x * kUmPos, l1 = min(L, l0 + kUmPos);
   float4 acc = make_float4(0, 0, 0, 0);
-  for (int l = l0; l < min(L, l0 + kUmPos); ++l) {
-    const int r = ids_restore ? static_cast<int>(ids_restore[static_cast<size_t>(b) * L + l]) : l;
-    const float4 v = *reinterpret_cast<const float4*>(g + (static_cast<size_t>(b) * L + l) * D + c);
-    if (r < T) {
-      *reinterpret_cast<uint2*>(du + (static_cast<size_t>(b) * T + r) * D + c) =
-          make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-    } else {
-      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+  for (int l = l0; l < l1; l += 4) {
+    int r[4];
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      r[j] = (l + j < l1) ? (ids_restore ? static_cast<int>(ids_restore[static_cast<size_t>(b) * L + l + j]) : l + j) : -1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (r[j] >= 0) v[j] = *reinterpret_cast<const float4*>(g + (static_cast<size_t>(b) * L + l + j) * D + c);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (r[j] < 0) continue;
+      if (r[j] < T) {
+        *reinterpret_cast<uint2*>(du + (static_cast<size_t>(b) * T + r[j]) * D + c) =
+            make_uint2(pack_bf16(v[j].x, v[j].y), pack_bf16(v[j].z, v[j].w));
+      } else {
+        acc.x += v[j].x, acc.y += v[j].y, acc.z += v[j].z, acc.w += v[j].w;
+      }
     }
   }
-  if (dmask_token) {
-    atomicAdd(dmask_token + c + 0, acc.x), atomicAdd(dmask_token + c + 1, acc.y);
-    atomicAdd(dmask_token + c + 2, acc.z), atomicAdd(dmask_token + c + 3, acc.w);
+  if (dmask_token) {  // one 16-byte reduction per thread and block (64 positions): [B * L / 64] per address
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dmask_token + c), "f"(acc.x), "f"(acc.y),
+                 "f"(acc.z), "f"(acc.w)
+                 : "memory");
   }
 }
 

@@ -15,6 +15,7 @@ struct GemmParams {
   int epi, act;
   int num_m_tiles, num_n_tiles, num_kb;
   int streamk;
+  int narrow_last;  // 1: the last column tile runs at half width (<= BLOCK_N/2 columns remain) - see UnitSched
   void* out;
   int ldo, out_fp32;
   const float* bias;

@@ -32,8 +32,16 @@ namespace mdt {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int kNumEpiWarps = 8;
-constexpr int kNumThreads = 128 + kNumEpiWarps * 32;  // 384
+#ifndef MDT_EPI_WARPS
+#define MDT_EPI_WARPS 8
+#endif
+// Epilogue warps per CTA (multiple of 4: warp w may only touch TMEM lanes 32*(w%4)..+31).  The 32-column chunks of a
+// tile are dealt to the kNumEpiWarps/4 warps of a lane group round robin.  With more than 8 the register file is
+// re-partitioned at kernel start (setmaxnreg: the producer/MMA warpgroup keeps 40 registers per thread).
+constexpr int kNumEpiWarps = MDT_EPI_WARPS;
+static_assert(kNumEpiWarps % 4 == 0 && kNumEpiWarps >= 4 && kNumEpiWarps <= 16, "epilogue warps: 4, 8, 12 or 16");
+constexpr int kNumThreads = 128 + kNumEpiWarps * 32;  // 384 (8 warps) / 512 (12) / 640 (16)
+constexpr int kEpiRegs = kNumEpiWarps == 12 ? 152 : (kNumEpiWarps == 16 ? 104 : 0);  // setmaxnreg.inc target
 
 template <int BLOCK_N, int CG>
 struct GemmCfg {
@@ -59,14 +67,21 @@ struct UnitSched {
   // groups work on the same k-slice of different tiles, so A/B panels are shared through L2 exactly as in a plain
   // tiled GEMM (a tile-major stream-K order made the wgrad GEMMs DRAM-bound: every unit streamed private panels).
   // splits == 1 is the ordinary persistent tile loop.
-  int num_kb, num_tiles, num_n_tiles, splits, grid;
+  // Tile order inside a slice: when the last column tile is a half-width one (N = 1152 = 4.5 x 256: every N = 1152
+  // GEMM of the encoder, 58 % of the GEMM flops) the full-width tiles are dealt first and the half-cost tiles last,
+  // continuing the same round robin - longest-processing-time-first.  With the plain (m, n) order a CTA pair's 8-9
+  // tiles contained 1-2 half tiles at random and the makespan was 8.5 tile-times for 7.78 of work (ncu launch list r01:
+  // fc2 263 us vs 240 us for the same-flop fc1 dgrad); now it is 8.0.
+  int num_kb, num_tiles, num_n_tiles, splits, grid, n_full, full_count;
   int unit, num_units;
-  int cur_tile, kb0, kb1;
+  int cur_tile, cur_m, cur_n, kb0, kb1;
   MDT_DEVINL void init(const GemmParams& p, int cg) {
     num_kb = p.num_kb;
     num_n_tiles = p.num_n_tiles;
     num_tiles = p.num_m_tiles * p.num_n_tiles;
     splits = p.streamk;  // number of k-slices (>= 1)
+    n_full = p.narrow_last ? p.num_n_tiles - 1 : p.num_n_tiles;
+    full_count = p.num_m_tiles * n_full;
     num_units = num_tiles * splits;
     grid = gridDim.x / cg;
     unit = blockIdx.x / cg;
@@ -75,13 +90,15 @@ struct UnitSched {
     if (unit >= num_units) return false;
     const int slice = unit / num_tiles;
     cur_tile = unit - slice * num_tiles;
+    if (cur_tile < full_count) cur_m = cur_tile / n_full, cur_n = cur_tile - cur_m * n_full;
+    else cur_m = cur_tile - full_count, cur_n = n_full;
     kb0 = static_cast<int>(static_cast<long long>(num_kb) * slice / splits);
     kb1 = static_cast<int>(static_cast<long long>(num_kb) * (slice + 1) / splits);
     unit += grid;
     return true;
   }
-  MDT_DEVINL int m_tile() const { return cur_tile / num_n_tiles; }
-  MDT_DEVINL int n_tile() const { return cur_tile % num_n_tiles; }
+  MDT_DEVINL int m_tile() const { return cur_m; }
+  MDT_DEVINL int n_tile() const { return cur_n; }
 };
 
 // ---- fused epilogue ---------------------------------------------------------------------------------------
@@ -265,17 +282,17 @@ MDT_DEVINL void epilogue_loop(const GemmParams& p, UnitSched& sched, uint64_t* t
                               uint64_t* tmem_empty_bar, uint32_t tmem_base, uint32_t stg, int warp, int cta_rank,
                               int lane) {
   constexpr int TILE_M = BLOCK_M * CG;
-  constexpr int kColsPerWarp = BLOCK_N / 2;  // 128 / 64
-  constexpr int kChunks = kColsPerWarp / 32;
+  constexpr int kParts = kNumEpiWarps / 4;  // warps sharing one TMEM lane group
+  constexpr int kTileChunks = BLOCK_N / 32;
   constexpr bool kHasOps = EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_GATE_RESID || EPI == EPI_DGELU;
   const int lane_group = warp & 3;       // tcgen05.ld: warp w may touch TMEM lanes 32*(w%4)..+31
-  const int col_half = (warp - 4) >> 2;  // 0/1
+  const int part = (warp - 4) >> 2;      // this warp takes chunks part, part + kParts, ... of the tile
   const int lcol = (lane & 7) * 4;
   auto tile_coord = [&](int mt, int nt, int& row_base, int& nrows, int& col_base) {
     row_base = mt * TILE_M + cta_rank * BLOCK_M + lane_group * 32;
     nrows = p.M - row_base;
     nrows = nrows > 32 ? 32 : nrows;
-    col_base = nt * BLOCK_N + col_half * kColsPerWarp;
+    col_base = nt * BLOCK_N;
   };
   int as = 0;
   uint32_t aphase = 0;
@@ -295,10 +312,9 @@ MDT_DEVINL void epilogue_loop(const GemmParams& p, UnitSched& sched, uint64_t* t
     }
     tcgen05_fence_after();
     MDT_GPROF(0)  // waiting for the accumulator
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * BLOCK_N +
-                           col_half * kColsPerWarp;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * BLOCK_N;
 #pragma unroll 1
-    for (int ci = 0; ci < kChunks; ++ci) {
+    for (int ci = part; ci < kTileChunks; ci += kParts) {
       const int col0 = col_base + ci * 32;
       const EpiCoord c = make_coord(p, row_base, nrows, col0 + lcol);
       EpiOps<EPI> ops;
@@ -405,6 +421,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   UnitSched sched;
   sched.init(p, CG);
 
+  if (warp < 4) {
+  // warpgroup 0: TMA producer, MMA issuer, TMEM allocator, one idle warp.  (With > 8 epilogue warps the register file is
+  // re-partitioned per warpgroup: ptxas budgets the code dominated by a setmaxnreg with that value, so the instruction
+  // sits at the top of each role branch and every warp of the warpgroup executes it.)
+  if constexpr (kEpiRegs > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer (every CTA) =====================
     int stage = 0;
@@ -502,8 +523,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
 #endif
 #undef MDT_MPROF
-  } else if (warp >= 4) {
+  }
+  } else {
     // ===================== epilogue (every CTA: its own 128 accumulator rows) =====================
+    if constexpr (kEpiRegs > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     const uint32_t stg = smem_u32(staging) + (warp - 4) * kStgFloats * 4;
 #define MDT_EPI_LOOP(E) \
   epilogue_loop<E, BLOCK_N, CG>(p, sched, tmem_full_bar, tmem_empty_bar, tmem_base, stg, warp, cta_rank, lane)
@@ -634,6 +657,7 @@ static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
   p.num_m_tiles = (a.M + TILE_M - 1) / TILE_M;
   p.num_n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
   p.num_kb = (a.K + BLOCK_K - 1) / BLOCK_K;
+  p.narrow_last = (BLOCK_N == 256 && p.num_n_tiles > 1 && (a.N - (p.num_n_tiles - 1) * BLOCK_N) <= BLOCK_N / 2) ? 1 : 0;
   p.out = a.out, p.ldo = a.ldo, p.out_fp32 = a.out_fp32;
   p.bias = a.bias;
   p.aux = a.aux, p.ld_aux = a.ld_aux;

@@ -276,3 +276,66 @@ def batches(dataset, batch, rank=0, world=1, start=0, pin=True):
             yb[j] = torch.from_numpy(y)
         yield zb, yb
         it += 1
+
+
+# ---- WebDataset shards (lmdb2wds.py:26, train_wds.py:58-64) ------------------------------------------------------------
+def write_wds_shard(path, moments, labels, start=0):
+    """One tar shard in the layout lmdb2wds.py writes: `<key>.latent` = pickle of the [2C,R,R] float32 array,
+    `<key>.cls` = the class index as ASCII (webdataset's default encoding of an int)."""
+    import io
+    import pickle
+    import tarfile
+    with tarfile.open(path, "w") as tf:
+        for i, (z, y) in enumerate(zip(moments, labels)):
+            key = f"{start + i:07d}"
+            for ext, payload in (("latent", pickle.dumps(np.ascontiguousarray(z, dtype=np.float32))),
+                                 ("cls", str(int(y)).encode())):
+                ti = tarfile.TarInfo(f"{key}.{ext}")
+                ti.size = len(payload)
+                tf.addfile(ti, io.BytesIO(payload))
+
+
+def wds_samples(shards, rank=0, world=1, num_classes=1000):
+    """Iterate (moments float32 [2C,R,R], one-hot float32 [num_classes]) over this rank's shards, forever
+    (train_wds.py:44-48 splits the shard list `data_list[rank::world]`; :58-64 decodes `latent` with pickle and `cls`
+    as a decimal string).  Pickle is executed: shards must be trusted, as in the reference."""
+    import pickle
+    import tarfile
+    mine = list(shards)[rank::world]
+    if not mine:
+        raise ValueError(f"{len(list(shards))} shards cannot be split over {world} ranks")
+    while True:
+        for path in mine:
+            with tarfile.open(path, "r") as tf:
+                cur, item = None, {}
+                for m in tf:
+                    if not m.isfile():
+                        continue
+                    key, _, ext = m.name.rpartition(".")
+                    if key != cur and item:
+                        item = {}
+                    cur = key
+                    item[ext] = tf.extractfile(m).read()
+                    if "latent" in item and "cls" in item:
+                        z = np.asarray(pickle.loads(item["latent"]), dtype=np.float32)
+                        onehot = np.zeros(num_classes, dtype=np.float32)
+                        onehot[int(item["cls"].decode("utf-8"))] = 1
+                        item = {}
+                        yield z, onehot
+
+
+def wds_batches(shards, batch, rank=0, world=1, num_classes=1000, pin=True):
+    """Drop-last batches of pinned host tensors from WebDataset shards (the loader train_wds.py:66-95 builds)."""
+    it = wds_samples(shards, rank, world, num_classes)
+    z0, y0 = next(it)
+    zb = torch.empty((batch, *z0.shape), dtype=torch.float32)
+    yb = torch.empty((batch, y0.shape[0]), dtype=torch.float32)
+    if pin and torch.cuda.is_available():
+        zb, yb = zb.pin_memory(), yb.pin_memory()
+    pending = [(z0, y0)]
+    while True:
+        for j in range(batch):
+            z, y = pending.pop() if pending else next(it)
+            zb[j] = torch.from_numpy(z)
+            yb[j] = torch.from_numpy(y)
+        yield zb, yb

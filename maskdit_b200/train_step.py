@@ -167,11 +167,10 @@ class TrainStep:
         self.side = torch.cuda.Stream(device=dev, priority=-1) if self.overlap else None
         self._done = []          # [lo, hi) ranges already handled in the current step
         self._lr_now = lr
-        # background optimizer: with overlap, a block's AdamW+EMA pass also runs on the side stream right after its
-        # exchange (HBM-bound work next to the tensor-bound backward, on the SMs the budget leaves free)
-        self.bg_opt = self.overlap and env.get("MDT_BG_OPT", "1") == "1"
-        self.bg_blocks = int(env.get("MDT_BG_BLOCKS", 8 * max(1, self.comm_ctas)))
-        net._grad_ready_hook = self._on_grads_ready if self.overlap else None
+        # (A background optimizer pass per block on the side stream was measured too, B200, 1 GPU, 4 / 2 SMs reserved:
+        # 129.0 / 130.5 ms per step against 121.8 ms - every SM taken from the persistent GEMM grids costs a whole tile
+        # wave, profiles/README.md - and removed.)
+        net._grad_ready_hook = self._on_grads_ready if (self.overlap and self.world > 1) else None
 
     # -- optimizer state for checkpoints (reference: train.py:259-270 stores optimizer.state_dict() under 'opt') ------
     def state_dict(self):
@@ -230,6 +229,13 @@ class TrainStep:
         self.lr, self.betas, self.eps, self.wd = group["lr"], tuple(group["betas"]), group["eps"], \
             group["weight_decay"]
 
+    def close(self):
+        """Release the communicator (a TrainStep owns one when world > 1 and collective == 'mdt')."""
+        if self.comm is not None:
+            self.comm.close()
+            self.comm = None
+        self.net._grad_ready_hook = None
+
     # -- gradient exchange + optimizer ------------------------------------------------------------------------------------
     def describe_collective(self):
         if self.world == 1:
@@ -271,8 +277,6 @@ class TrainStep:
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
             self._exchange(lo, hi)
-            if self.bg_opt:
-                self._step_range(lo, hi, max_blocks=self.bg_blocks)
         self._done.append((lo, hi))
 
     def _fwd_bwd_graphed(self, images, labels, mask_ratio, mae_loss_coef, loss_call, moments=False):
@@ -377,12 +381,9 @@ class TrainStep:
                 cur = 0
                 for lo, hi in sorted(self._done) + [(st.n_train, st.n_train)]:   # the complement of the block ranges
                     self._exchange(cur, lo)
-                    if self.bg_opt:
-                        self._step_range(cur, lo)
                     cur = max(cur, hi)
             main.wait_stream(self.side)
-            if not self.bg_opt:
-                self._step_range(0, st.n_train)      # ONE optimizer pass over the whole (reduced) buffer
+            self._step_range(0, st.n_train)          # ONE optimizer pass over the whole (reduced) buffer
         elif self.world == 1:
             self._step_range(0, st.n_train)
         elif self.ar_chunks > 1:

@@ -86,3 +86,25 @@ def test_rank_seed_batches_and_png(tmp_path):
     n = struct.unpack(">I", raw[i - 4:i])[0]
     rows = np.frombuffer(zlib.decompress(raw[i + 4:i + 4 + n]), np.uint8).reshape(16, 1 + 8 * 3)
     assert np.array_equal(rows[:, 1:].reshape(16, 8, 3), img) and not rows[:, 0].any()
+
+
+def test_webdataset_shards_roundtrip(tmp_path):
+    """lmdb2wds.py:26 layout (`<key>.latent` pickle, `<key>.cls` ASCII) -> train_wds.py:58-64 decoding, shards split by rank."""
+    rng = np.random.default_rng(2)
+    moments = rng.standard_normal((12, 8, 4, 4)).astype(np.float32)
+    labels = rng.integers(0, 10, 12)
+    paths = []
+    for s in range(3):
+        p = str(tmp_path / f"latent-{s:04d}.tar")
+        D.write_wds_shard(p, moments[4 * s:4 * s + 4], labels[4 * s:4 * s + 4], start=4 * s)
+        paths.append(p)
+    it = D.wds_samples(paths, rank=0, world=1, num_classes=10)
+    for i in range(14):                                       # 12 samples, then the epoch wraps around
+        z, y = next(it)
+        assert np.array_equal(z, moments[i % 12]) and y.argmax() == labels[i % 12] and y.sum() == 1
+    it1 = D.wds_samples(paths, rank=1, world=2, num_classes=10)          # data_list[rank::world] -> shard 1 only
+    assert np.array_equal(next(it1)[0], moments[4])
+    zb, yb = next(D.wds_batches(paths, 5, num_classes=10, pin=False))
+    assert torch.equal(zb, torch.from_numpy(moments[:5])) and yb.argmax(1).tolist() == labels[:5].tolist()
+    with pytest.raises(ValueError):
+        next(D.wds_samples(paths[:1], rank=1, world=2))

@@ -20,3 +20,10 @@ MDT_OVERLAP=1 MDT_COMM_CTAS=4 timeout 600 python bench.py --steps 10 --warmup 3 
 import json,sys; d=json.loads([l for l in sys.stdin.read().splitlines() if l.startswith('{')][-1]); print('N=1 background optimizer, 4 SMs reserved:', round(d['value'],1), 'samples/s', round(d['ms_per_step'],2), 'ms')"
 MDT_OVERLAP=1 MDT_COMM_CTAS=2 MDT_BG_BLOCKS=32 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-sub 2>/dev/null | python -c "
 import json,sys; d=json.loads([l for l in sys.stdin.read().splitlines() if l.startswith('{')][-1]); print('N=1 background optimizer, 2 SMs reserved:', round(d['value'],1), 'samples/s', round(d['ms_per_step'],2), 'ms')"
+# GEMM epilogue-warp variants (8 default / 12 / 16): per-shape in-step timing + step time, same box
+for v in "" _e12 _e16; do
+  echo "== GEMM variant [${v:-e8}]"
+  MDT_ENGINE=py MDT_LIB_PATH=$PWD/maskdit_b200/libmaskdit_b200$v.so timeout 600 python tools/gemm_shapes_step.py 256 32 2>&1 | head -34
+  MDT_LIB_PATH=$PWD/maskdit_b200/libmaskdit_b200$v.so timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-sub 2>/dev/null | python -c "
+import json,sys; d=json.loads([l for l in sys.stdin.read().splitlines() if l.startswith('{')][-1]); print('step [${v:-e8}]', round(d['value'],1), 'samples/s', round(d['ms_per_step'],2), 'ms, gemm frac', round(d['roofline']['frac'],3), 'clk', d['clocks']['sm_mhz'])"
+done

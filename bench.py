@@ -152,10 +152,40 @@ def cpu_reference_train(B, steps, warmup, R=32):
     return B * len(times) / sum(times), sum(times)
 
 
-def cpu_baseline_record(steps, warmup, R=32, B=8):
+def cpu_reference_eval(R=32):
+    """XL/2 masked forward at B=2, fp32; (iii) sampler at B=2, CFG 1.5: three network
+    evaluations are timed and scaled to the 35 of an 18-step run (the sampler is 35 identical evaluations + axpys)."""
+    from oracle import maskdit_oracle as O
+    cfg = O.Cfg(model_type="DiT-XL/2", img_resolution=R, num_classes=1000)
+    sd = O.make_state_dict(cfg, 1)
+    g = torch.Generator().manual_seed(0)
+    B = 2
+    x = torch.randn(B, 4, R, R, generator=g) * 0.5
+    y = torch.nn.functional.one_hot(torch.randint(0, 1000, (B,), generator=g), 1000).float()
+    md = O.mask_from_noise(torch.rand(B, cfg.num_patches, generator=g), 0.5)
+    with torch.no_grad():
+        O.edm_loss(sd, cfg, x, y, torch.randn(B, 1, 1, 1, generator=g), torch.randn(x.shape, generator=g), md, 0.1)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            O.edm_loss(sd, cfg, x, y, torch.randn(B, 1, 1, 1, generator=g), torch.randn(x.shape, generator=g), md, 0.1)
+        fwd = 2 * B / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for s_ in (80.0, 10.0, 0.5):
+            O.edm_precond(sd, cfg, x, torch.tensor(s_, dtype=torch.float64), y, cfg_scale=1.5, training=False)
+        per_eval = (time.perf_counter() - t0) / 3
+    return fwd, B / (35 * per_eval)
+
+
+def cpu_baseline_record(steps, warmup, R=32, B=8, extras=False):
     threads, how = pin_to_one_socket()
     sps, secs = cpu_reference_train(B, steps, warmup, R=R)
-    return sps, secs, {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "same_config": False,
+    extra = {}
+    if extras:
+        fwd, ips = cpu_reference_eval(R)
+        extra = {"c1_forward_b2": {"value": fwd, "unit": "samples/s"},
+                 "c5_sampler_b2_scaled": {"value": ips, "unit": "img/s",
+                                          "how": "3 CFG network evaluations at B=2 timed, scaled to the 35 of an 18-step run"}}
+    return sps, secs, {**extra, "value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "same_config": False,
                        "sample": f"{steps} timed steps (+{warmup} warm-up) of batch {B} (SURVEY 8d), EDM loss fwd + bwd + "
                                  f"AdamW, torch CPU fp32, {threads} threads {how}; host has {os.cpu_count()} logical "
                                  f"CPUs; {secs:.1f} s timed.  /root/reference is not on the GPU box: the oracle port "
@@ -282,8 +312,16 @@ def main():
             del net64
             torch.cuda.empty_cache()
             line["sub"] = sub
+        if world > 1 and not args.no_sub and args.workload == "train256" and args.batch_per_gpu is None:
+            # the same step with the bf16 gradient-exchange buffer (SURVEY 8e allows it; fp32 stays the default)
+            os.environ["MDT_GRAD_AR"] = "bf16"
+            net2 = build_xl2(32, dev)
+            line.setdefault("sub", {})["c2_bf16_grad_exchange"] = bench_train(args, net2, env, 32, PK, 256,
+                                                                           max(5, args.steps // 2), 3, full=False)
+            del os.environ["MDT_GRAD_AR"], net2
+            torch.cuda.empty_cache()
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            _, _, line["cpu_baseline"] = cpu_baseline_record(3, 1, R=R, B=8 if R == 32 else 2)
+            _, _, line["cpu_baseline"] = cpu_baseline_record(3, 1, R=R, B=8 if R == 32 else 2, extras=(R == 32))
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -335,7 +373,8 @@ def bench_train(args, net, env, R, PK, B, steps, warmup, full):
     if not full:
         rec = {"metric": "train_samples_per_sec", "value": sps, "unit": "samples/s", "n_gpus": world, "steps": steps,
                "warmup": warmup, "ms_per_step": ms_step, "gpu_launches": launches,
-               "config": {"workload": workload, "batch_per_gpu": B, "global_batch": B * world},
+               "config": {"workload": workload, "batch_per_gpu": B, "global_batch": B * world,
+                          "grad_allreduce": ts.describe_collective()},
                "roofline": {"bound": "tensor", "step_achieved": step_tf, "peak": PK["sustained"], "unit": "TFLOP/s",
                             "step_frac": step_tf / PK["sustained"], "peak_source": f"{PK['src']} sustained bf16"}}
         ts.close()

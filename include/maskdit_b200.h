@@ -42,10 +42,12 @@ int mdt_gemm_configs_seen(int reset);
  *               = 1: operand stored [K, rows] with rows contiguous ("MN-major")
  * ------------------------------------------------------------------------------------------------------------ */
 enum { MDT_EPI_STORE = 0,      /* out = act(acc + bias [+ resid])            out bf16 or fp32            */
-       MDT_EPI_GELU = 1,       /* aux = bf16(acc+bias); out = bf16(gelu_tanh(aux))      (Mlp.fc1 + act)   */
+       MDT_EPI_GELU = 1,       /* h = bf16(acc+bias); out = bf16(gelu_tanh(h)); aux (optional) = bf16(gelu_tanh'(h))
+                                  (Mlp.fc1 + act; aux is what the backward needs of h)                    */
        MDT_EPI_GATE_RESID = 2, /* y = acc+bias; aux = bf16(y) (optional); out_f32 = resid + gate[row/rpg]*y
                                   (DiTBlock residual update, models/maskdit.py:190-191)                   */
-       MDT_EPI_DGELU = 3,      /* out = bf16(acc * gelu_tanh'(aux))          (backward through GELU)      */
+       MDT_EPI_DGELU = 3,      /* out = bf16(acc * aux), aux = the gelu' tensor MDT_EPI_GELU stored (backward
+                                  through GELU)                                                           */
        MDT_EPI_ATOMIC = 4 };   /* out_f32 += acc via red.global.add, stream-K schedule (wgrad, long-K)    */
 enum { MDT_ACT_NONE = 0, MDT_ACT_SILU = 1 };
 

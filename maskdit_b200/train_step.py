@@ -160,10 +160,10 @@ class TrainStep:
         self._sms = torch.cuda.get_device_properties(dev).multi_processor_count
         self.graph = (os.environ.get("MDT_TRAIN_GRAPH", "0") == "1") if graph is None else bool(graph)
         self._graphs = {}
-        # gradient all-reduce in this many chunks, pipelined against the optimizer pass (world > 1).  Default 1 = one
-        # flat call: measured on 2 x B200 (same box) 132.0 ms/step flat vs 133.3 ms with 8 chunks - the all-reduce and
-        # the AdamW/EMA pass are both HBM-bound, so running them side by side buys nothing.
-        self.ar_chunks = int(os.environ.get("MDT_AR_CHUNKS", "1"))
+        # gradient all-reduce in this many chunks on a side stream, the fused AdamW/EMA pass of chunk k running while
+        # chunk k+1 is on the wire.  Measured on 4 x B200 (profiles/r02_experiments.md): 131.65 ms/step flat, 130.71 with
+        # 4 chunks (fp32); 129.16 -> 128.31 (bf16 buffer); 8 chunks 128.79.  (At 2 GPUs in round 1: neutral.)
+        self.ar_chunks = int(os.environ.get("MDT_AR_CHUNKS", "4"))
         self.side = torch.cuda.Stream(device=dev, priority=-1) if self.overlap else None
         self._done = []          # [lo, hi) ranges already handled in the current step
         self._lr_now = lr
@@ -242,7 +242,9 @@ class TrainStep:
             return "none (1 GPU)"
         how = "own NCCL communicator behind the C ABI (mdt_allreduce_grads)" if self.comm else "torch.distributed"
         when = (f"per block during the backward on a side stream ({self.comm_ctas} comm CTAs, persistent grids sized "
-                f"for {self._sms - self.comm_ctas} SMs)") if self.overlap else "one flat call after the backward"
+                f"for {self._sms - self.comm_ctas} SMs)") if self.overlap else (
+            f"after the backward in {self.ar_chunks} chunks on a side stream, pipelined with the optimizer pass"
+            if self.ar_chunks > 1 else "one flat call after the backward")
         return f"{self.grad_dtype} sum-all-reduce of the flat gradient buffer, {how}, {when}"
 
     def _exchange(self, lo, hi):

@@ -79,18 +79,19 @@ def test_gemm_epilogues(ops):
     o16 = torch.empty(M, N, device=dev(), dtype=torch.bfloat16)
     aux = torch.empty(M, N, device=dev(), dtype=torch.bfloat16)
     ops.gemm(A, B, M, N, K, out=o16, bias=bias, epi=ops.EPI_GELU, aux=aux, ld_aux=N)
-    close(aux, acc, 2 ** -8, "gelu pre")
-    close(o16, F.gelu(aux.float(), approximate="tanh"), 2 ** -7, "gelu out")
+    hb = acc.to(torch.bfloat16).float().requires_grad_(True)     # the pre-activation as a bf16 nn.Linear would emit it
+    gel = F.gelu(hb, approximate="tanh")
+    gel.sum().backward()
+    close(o16, gel.detach(), 2 ** -7, "gelu out")
+    close(aux, hb.grad, 2 ** -7, "gelu' (aux)")                  # aux = gelu'(h): all the backward needs of h
     gate = torch.randn(M // T, N, device=dev())
     ops.gemm(A, B, M, N, K, out=out, bias=bias, epi=ops.EPI_GATE_RESID, aux=aux, ld_aux=N, resid=R, ld_resid=N,
              gate=gate, ld_gate=N, rows_per_group=T)
     close(aux, acc, 2 ** -8, "gate_resid y")
     close(out, R + gate.repeat_interleave(T, 0) * acc, 1e-3, "gate_resid out")
-    h = rb(M, N)
+    h = rb(M, N)                                                 # stands for the stored gelu' tensor
     ops.gemm(A, B, M, N, K, out=o16, epi=ops.EPI_DGELU, aux=h, ld_aux=N)
-    hf = h.float().requires_grad_(True)
-    F.gelu(hf, approximate="tanh").sum().backward()
-    close(o16, (A.float() @ B.float().t()) * hf.grad, 2 ** -7, "dgelu")
+    close(o16, (A.float() @ B.float().t()) * h.float(), 2 ** -7, "dgelu")
     # fused bias gradient: colsum[n] += sum_m of the STORED (bf16-rounded) outputs, incl. a ragged N (1000) and odd M
     for (m2, n2) in ((M, N), (300, 1000)):
         A2, B2, h2 = rb(m2, K), rb(n2, K, scale=0.05), rb(m2, n2)
@@ -414,3 +415,22 @@ def test_heun_and_adamw(ops):
     close(ema.cpu(), er, 1e-6, "ema")
     close(v.cpu(), vr, 1e-4, "adamw v")
     assert torch.equal(w16, w.to(torch.bfloat16))
+
+
+def test_sampler_tail_uint8_and_lincomb(ops):
+    """sample.py:287: images.add_(1).mul(127.5).clamp_(0, 255).to(uint8).permute(0, 2, 3, 1) — bit-exact; and the fp64
+    linear-combination kernel of the ablation sampler."""
+    torch.manual_seed(12)
+    img = (torch.randn(3, 3, 16, 8, device=dev()) * 0.8)
+    img[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, -3.0, 3.0], device=dev())
+    got = ops.to_uint8_nhwc(img.contiguous())
+    ref = img.clone().add_(1).mul(127.5).clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1)
+    assert torch.equal(got, ref)
+    x, y = torch.randn(1000, device=dev(), dtype=torch.float64), torch.randn(1000, device=dev(), dtype=torch.float64)
+    z = torch.randn(1000, device=dev())
+    out, o32 = torch.empty_like(x), torch.empty(1000, device=dev())
+    ops.lincomb_f64(0.3, x, -1.7, y, 2.5, z, out=out, out_f32=o32, f32_scale=0.5)
+    want = 0.3 * x - 1.7 * y + 2.5 * z.double()
+    assert torch.allclose(out, want, rtol=1e-14, atol=1e-14) and torch.allclose(o32, (want * 0.5).float(), rtol=1e-6)
+    ops.lincomb_f64(2.0, x, out=x)                                   # in place, x only
+    assert torch.allclose(x, want * 0 + x)                           # finite, no aliasing fault

@@ -18,7 +18,7 @@ timeout 900 python bench.py > gpurun_out/r02_bench_default.json 2> gpurun_out/r0
 echo "bench exit $?"; cut -c1-6000 gpurun_out/r02_bench_default.json
 MDT_OVERLAP=1 MDT_COMM_CTAS=4 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-sub 2>/dev/null | python -c "
 import json,sys; d=json.loads([l for l in sys.stdin.read().splitlines() if l.startswith('{')][-1]); print('N=1 background optimizer, 4 SMs reserved:', round(d['value'],1), 'samples/s', round(d['ms_per_step'],2), 'ms')"
-MDT_OVERLAP=1 MDT_COMM_CTAS=2 MDT_BG_BLOCKS=32 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-sub 2>/dev/null | python -c "
+MDT_OVERLAP=1 MDT_COMM_CTAS=2 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-sub 2>/dev/null | python -c "
 import json,sys; d=json.loads([l for l in sys.stdin.read().splitlines() if l.startswith('{')][-1]); print('N=1 background optimizer, 2 SMs reserved:', round(d['value'],1), 'samples/s', round(d['ms_per_step'],2), 'ms')"
 # GEMM epilogue-warp variants (8 default / 12 / 16): per-shape in-step timing + step time, same box
 for v in "" _e12 _e16; do

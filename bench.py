@@ -313,10 +313,10 @@ def main():
             torch.cuda.empty_cache()
             line["sub"] = sub
         if world > 1 and not args.no_sub and args.workload == "train256" and args.batch_per_gpu is None:
-            # the same step with the bf16 gradient-exchange buffer (SURVEY 8e allows it; fp32 stays the default)
-            os.environ["MDT_GRAD_AR"] = "bf16"
+            # the same step with the fp32 gradient exchange (DDP's arithmetic) next to the default bf16 exchange buffer
+            os.environ["MDT_GRAD_AR"] = "fp32"
             net2 = build_xl2(32, dev)
-            line.setdefault("sub", {})["c2_bf16_grad_exchange"] = bench_train(args, net2, env, 32, PK, 256,
+            line.setdefault("sub", {})["c2_fp32_grad_exchange"] = bench_train(args, net2, env, 32, PK, 256,
                                                                            max(5, args.steps // 2), 3, full=False)
             del os.environ["MDT_GRAD_AR"], net2
             torch.cuda.empty_cache()

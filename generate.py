@@ -6,9 +6,10 @@ unchanged: same state-dict keys), and runs `edm_sampler` on the B200 engine for 
 per-sample generators (utils.StackedRandomGenerator, utils.py:119-133).  Under torchrun the seed batches are dealt
 to the ranks exactly as generate_with_net does (sample.py:232-235: rank-strided, one barrier per batch); giving any of
 --solver / --discretization / --schedule / --scaling selects `ablation_sampler` (sample.py:243-245).  The SD-VAE
-decode of the reference (sample.py:275, a separate convolutional network) is outside the accelerated path (SURVEY.md
-§2): latents are saved as `.npy` per seed; the 8-bit conversion + PNG writing of sample.py:287-296 exist
-(`ops.to_uint8_nhwc`, `sampler.write_png`) and `--png_preview` applies them to the raw latent channels.
+decode of the reference (sample.py:275) runs on the same kernels (`maskdit_b200/vae.py`) when `--pretrained_path` names a
+FrozenAutoencoderKL checkpoint: images are converted to 8 bit (`ops.to_uint8_nhwc`) and written as `<seed>.png`
+(`sampler.write_png`), exactly the tail of generate_with_net (sample.py:275-296).  The latents are always saved as `.npy`
+per seed as well; without a VAE checkpoint `--png_preview` writes the raw latent channels as a picture.
 """
 import argparse
 import os
@@ -51,6 +52,10 @@ def main():
     ap.add_argument("--discretization", choices=["vp", "ve", "iddpm", "edm"], default=None)
     ap.add_argument("--schedule", choices=["vp", "ve", "linear"], default=None)
     ap.add_argument("--scaling", choices=["vp", "none"], default=None)
+    ap.add_argument("--pretrained_path", default=None,
+                    help="SD-VAE checkpoint (FrozenAutoencoderKL state dict, reference default assets/vae/autoencoder_kl.pth): "
+                         "decode the latents and write PNGs as generate_with_net does (sample.py:275-296)")
+    ap.add_argument("--subdirs", action="store_true", help="<seed - seed % 1000:06d>/ sub-directories (sample.py:289)")
     ap.add_argument("--png_preview", action="store_true",
                     help="also write channels 0-2 of every latent as an 8-bit PNG (no SD-VAE in this repo)")
     args, _ = ap.parse_known_args()
@@ -67,6 +72,10 @@ def main():
         ck = torch.load(args.ckpt_path, map_location=device, weights_only=False)
         net.load_state_dict({k.replace("_orig_mod.", ""): v for k, v in ck["ema"].items()})
     os.makedirs(args.results_dir, exist_ok=True)
+    vae = None
+    if args.pretrained_path:
+        from maskdit_b200.vae import get_model
+        vae = get_model(args.pretrained_path, device=device)
     kw = {k: getattr(args, k) for k in ("solver", "discretization", "schedule", "scaling") if getattr(args, k)}
     sampler_fn = ablation_sampler if kw else edm_sampler          # sample.py:243-245
     n_done = 0
@@ -84,7 +93,13 @@ def main():
         with torch.no_grad():
             z = sampler_fn(net, latents.float(), labels.float(), cfg_scale=args.cfg_scale,
                            randn_like=rnd.randn_like, num_steps=args.num_steps, S_churn=args.S_churn, **kw).float()
-        if args.png_preview:
+        if vae is not None:       # images = vae.decode(z); add(1).mul(127.5).clamp(0,255).to(uint8) NHWC; PNG per seed
+            px = ops.to_uint8_nhwc(vae.decode(z).contiguous()).cpu().numpy()
+            for s, im in zip(bs, px):
+                d = os.path.join(args.results_dir, f"{s - s % 1000:06d}") if args.subdirs else args.results_dir
+                os.makedirs(d, exist_ok=True)
+                write_png(os.path.join(d, f"{s:06d}.png"), im)
+        elif args.png_preview:
             px = ops.to_uint8_nhwc((z[:, :3] / z[:, :3].abs().amax().clamp_min(1e-8)).contiguous()).cpu().numpy()
             for s, im in zip(bs, px):
                 write_png(os.path.join(args.results_dir, f"{s:06d}.png"), im)

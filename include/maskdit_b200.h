@@ -42,12 +42,10 @@ int mdt_gemm_configs_seen(int reset);
  *               = 1: operand stored [K, rows] with rows contiguous ("MN-major")
  * ------------------------------------------------------------------------------------------------------------ */
 enum { MDT_EPI_STORE = 0,      /* out = act(acc + bias [+ resid])            out bf16 or fp32            */
-       MDT_EPI_GELU = 1,       /* h = bf16(acc+bias); out = bf16(gelu_tanh(h)); aux (optional) = bf16(gelu_tanh'(h))
-                                  (Mlp.fc1 + act; aux is what the backward needs of h)                    */
+       MDT_EPI_GELU = 1,       /* aux = bf16(acc+bias); out = bf16(gelu_tanh(aux))      (Mlp.fc1 + act)   */
        MDT_EPI_GATE_RESID = 2, /* y = acc+bias; aux = bf16(y) (optional); out_f32 = resid + gate[row/rpg]*y
                                   (DiTBlock residual update, models/maskdit.py:190-191)                   */
-       MDT_EPI_DGELU = 3,      /* out = bf16(acc * aux), aux = the gelu' tensor MDT_EPI_GELU stored (backward
-                                  through GELU)                                                           */
+       MDT_EPI_DGELU = 3,      /* out = bf16(acc * gelu_tanh'(aux))          (backward through GELU)      */
        MDT_EPI_ATOMIC = 4 };   /* out_f32 += acc via red.global.add, stream-K schedule (wgrad, long-K)    */
 enum { MDT_ACT_NONE = 0, MDT_ACT_SILU = 1 };
 
@@ -298,6 +296,27 @@ int mdt_nccl_unique_id(void* id128);
 int mdt_nccl_comm_create(const void* id128, int rank, int world, int max_ctas, void** comm);
 int mdt_nccl_comm_destroy(void* comm);
 int mdt_allreduce_grads(void* comm, void* grad, long long n, int bf16, void* stream);
+
+/* ============================================================================================================
+ * Sampler tail: SD-VAE decode (sample.py:275 `vae.decode(z)`; autoencoder.py:306-453).  Activations are pixel-major
+ * fp32 row matrices [B*H*W, C]; every convolution is mdt_gemm_bf16 on an im2col operand built by mdt_vae_im2col with
+ * the GroupNorm(32) affine, the swish and the nearest-2x upsample of its source fused in.  The host sequencing is
+ * maskdit_b200/vae.py (same state-dict keys as FrozenAutoencoderKL: `decoder.*`, `post_quant_conv.*`).
+ * ============================================================================================================ */
+/* out [B*P, C] f32 = post_quant_conv(z / scale_factor), z [B,C,h,w] NCHW (autoencoder.py:449-451); C <= 8           */
+int mdt_vae_post_quant(const float* z, const float* W, const float* bias, float scale_factor, float* out, int B,
+                       int C, int P, void* stream);
+/* GroupNorm(32) statistics (Normalize, autoencoder.py:34-35) of x [B,P,C] f32: sums [B,32,2] f64 = (sum, sum of squares) */
+int mdt_vae_gn_stats(const float* x, double* sums, int B, int P, int C, void* stream);
+/* A [B*H*W, Kp] bf16, A[(b,y,x),(ky,kx,c)] = f(src[b,(y+ky-pad)/up,(x+kx-pad)/up,c]) (0 outside); ks = 1 | 3; up = 1 | 2;
+ * f = identity (sums NULL) | GroupNorm affine | GroupNorm affine + swish (silu != 0): ResnetBlock / Upsample /
+ * norm_out inputs (autoencoder.py:49-53,117-137,404-406); columns >= ks*ks*C are zero.                              */
+int mdt_vae_im2col(const float* src, const double* sums, const float* gamma, const float* beta, int silu, int ks,
+                   int up, void* A_bf16, int B, int H, int W, int C, int Kp, void* stream);
+/* P [rows, cols] bf16 = softmax(scale * S) along columns (AttnBlock, autoencoder.py:185-187)                        */
+int mdt_vae_softmax_rows(const float* S, float scale, void* P_bf16, int rows, int cols, void* stream);
+/* x [B,P,ldx] f32 (first C columns) -> out [B,C,P] f32: the NCHW image `decode` returns                             */
+int mdt_vae_rows_to_nchw(const float* x, float* out, int B, int P, int C, int ldx, void* stream);
 
 #ifdef __cplusplus
 }

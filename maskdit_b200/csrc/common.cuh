@@ -59,17 +59,6 @@ MDT_DEVINL float gelu_tanh_grad(float x) {
   // 0.5 (1 + t) + 0.5 x (1 - t^2) du
   return fmaf((0.5f * x) * du, fmaf(-t, t, 1.f), fmaf(0.5f, t, 0.5f));
 }
-// GELU and its derivative with ONE tanh: the forward fc1 epilogue stores gelu'(h) (bf16) instead of h, so the backward
-// epilogue only multiplies (the dGELU GEMM ran at 1043 TF/s in-step against 1321 for the same-shape plain dgrad:
-// 10 instructions + a MUFU per element on 8 epilogue warps - profiles/r02_experiments.md).
-MDT_DEVINL void gelu_tanh_both(float x, float& g, float& dg) {
-  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
-  const float x2 = x * x;
-  const float t = tanh_fast(x * fmaf(x2, k01, k0));
-  const float hx = 0.5f * x;
-  g = fmaf(hx, t, hx);
-  dg = fmaf(hx * fmaf(x2, 3.f * k01, k0), fmaf(-t, t, 1.f), fmaf(0.5f, t, 0.5f));
-}
 // 2^x as ONE MUFU.EX2 (ex2.approx.ftz, 2 ulp): exp2f() wraps the same instruction in a denormal-range rescale
 // (4 more instructions per element; ncu r01: 43 % of all instructions of the attention forward).  Softmax arguments
 // are <= 0 and results below 2^-126 flush to zero, which bf16 P cannot represent anyway.

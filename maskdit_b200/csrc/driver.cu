@@ -160,7 +160,7 @@ struct Arena {
   }
 };
 
-struct BlockBuf {  // hpre = gelu'(fc1 pre-activation) as stored by the EPI_GELU epilogue (what EPI_DGELU multiplies by)
+struct BlockBuf {
   i64 xm1, mean1, rstd1, qkv, O, lse, X1, y1, xm2, mean2, rstd2, a, hpre, X2, y2;
 };
 

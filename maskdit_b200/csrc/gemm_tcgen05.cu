@@ -201,14 +201,13 @@ MDT_DEVINL void epilogue_chunk(const GemmParams& p, uint32_t stg, const EpiCoord
         if (p.act == ACT_SILU) v = make_float4(silu(v.x), silu(v.y), silu(v.z), silu(v.w));
         if (p.out_fp32) stg128(ao, v); else stg64(ao, pack4_bf16(v));
       } else if constexpr (EPI == EPI_GELU) {
-        // pre-activation is rounded to bf16 first (as a bf16 nn.Linear output would be), GELU on the rounded value;
-        // aux receives gelu'(h) - all the backward needs of h - computed from the same tanh
-        const float4 h = unpack4_bf16(pack4_bf16(v));
-        float4 g, d;
-        gelu_tanh_both(h.x, g.x, d.x), gelu_tanh_both(h.y, g.y, d.y);
-        gelu_tanh_both(h.z, g.z, d.z), gelu_tanh_both(h.w, g.w, d.w);
-        if (p.aux) stg64(a_aux + i * s_aux, pack4_bf16(d));
-        stg64(ao, pack4_bf16(g));
+        // pre-activation is rounded to bf16 first (as a bf16 nn.Linear output would be), GELU on the rounded value
+        // (storing gelu'(h) here instead, so that the backward epilogue only multiplies, was measured: the forward GEMM
+        // went 286 -> 333 us, the dGELU GEMM 333 -> 300 us - a net loss, profiles/r02_experiments.md section 7)
+        const uint2 pre = pack4_bf16(v);
+        if (p.aux) stg64(a_aux + i * s_aux, pre);
+        const float4 h = unpack4_bf16(pre);
+        stg64(ao, pack4_bf16(make_float4(gelu_tanh(h.x), gelu_tanh(h.y), gelu_tanh(h.z), gelu_tanh(h.w))));
       } else if constexpr (EPI == EPI_GATE_RESID) {
         if (p.aux) stg64(a_aux + i * s_aux, pack4_bf16(v));
         float4 g = o.gate4;
@@ -219,8 +218,9 @@ MDT_DEVINL void epilogue_chunk(const GemmParams& p, uint32_t stg, const EpiCoord
         const float4 r = o.res[i];  // may alias `out` (in-place residual update): each element is read before written
         stg128(ao, make_float4(fmaf(g.x, v.x, r.x), fmaf(g.y, v.y, r.y), fmaf(g.z, v.z, r.z), fmaf(g.w, v.w, r.w)));
       } else if constexpr (EPI == EPI_DGELU) {
-        const float4 d = unpack4_bf16(o.auxv[i]);  // gelu'(h), stored by the forward epilogue
-        const uint2 ov = pack4_bf16(make_float4(v.x * d.x, v.y * d.y, v.z * d.z, v.w * d.w));
+        const float4 h = unpack4_bf16(o.auxv[i]);
+        const uint2 ov = pack4_bf16(make_float4(v.x * gelu_tanh_grad(h.x), v.y * gelu_tanh_grad(h.y),
+                                                v.z * gelu_tanh_grad(h.z), v.w * gelu_tanh_grad(h.w)));
         stg64(ao, ov);
         const float4 r = unpack4_bf16(ov);  // sum what was stored (what a separate column-sum pass would read back)
         cs.x += r.x, cs.y += r.y, cs.z += r.z, cs.w += r.w;
@@ -256,17 +256,16 @@ __device__ __noinline__ void epilogue_ragged(const GemmParams& p, uint32_t stg, 
           if (p.out_fp32) *o32 = v; else *o16 = __float2bfloat16_rn(v);
           break;
         case EPI_GELU: {
-          float g, d;
-          gelu_tanh_both(__bfloat162float(__float2bfloat16_rn(v)), g, d);
-          if (p.aux) *aux = __float2bfloat16_rn(d);
-          *o16 = __float2bfloat16_rn(g);
+          const __nv_bfloat16 pre = __float2bfloat16_rn(v);
+          if (p.aux) *aux = pre;
+          *o16 = __float2bfloat16_rn(gelu_tanh(__bfloat162float(pre)));
         } break;
         case EPI_GATE_RESID:
           if (p.aux) *aux = __float2bfloat16_rn(v);
           *o32 = fmaf(p.gate[(row / p.rows_per_group) * p.ld_gate + c], v, p.resid[row * p.ld_resid + c]);
           break;
         case EPI_DGELU: {
-          const __nv_bfloat16 r = __float2bfloat16_rn(v * __bfloat162float(*aux));
+          const __nv_bfloat16 r = __float2bfloat16_rn(v * gelu_tanh_grad(__bfloat162float(*aux)));
           *o16 = r;
           if (p.colsum) atomicAdd(p.colsum + c, __bfloat162float(r));
         } break;

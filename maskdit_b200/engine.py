@@ -158,7 +158,7 @@ class Engine:
         xm2, mean2, rstd2 = ops.ln_modulate(X1, mod[:, o + 3 * D:], mod[:, o + 4 * D:], NA, T, M, D, save_stats=save)
         H4 = self.store.offsets[f"{p}.mlp.fc1.weight"][2][0]
         a = torch.empty(M, H4, dtype=bf16, device=dev)
-        hpre = torch.empty(M, H4, dtype=bf16, device=dev) if save else None   # receives gelu'(fc1 output), see EPI_GELU
+        hpre = torch.empty(M, H4, dtype=bf16, device=dev) if save else None
         gemm(xm2, self.w16(f"{p}.mlp.fc1.weight"), M, H4, D, out=a, bias=self.w32(f"{p}.mlp.fc1.bias"), epi=EPI_GELU,
              aux=hpre, ld_aux=H4)
         X2 = torch.empty(M, D, dtype=f32, device=dev) if save else X1

@@ -263,6 +263,32 @@ def ablation_case(name, cfg, B):
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
 
 
+def vae_case(name):
+    """SD-VAE decode (autoencoder.py:449-453; the sampler tail, sample.py:275,287) by the unmodified reference module
+    with the stand-in weights of oracle.vae_oracle.make_vae_state_dict: 8x8 latents -> 64x64 images."""
+    import io
+    import contextlib
+    import tempfile
+    import autoencoder as ra
+    from oracle import vae_oracle as VO
+    sd = VO.make_vae_state_dict(3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        dec = ra.Decoder(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
+                         ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0).eval()
+    dsd = {k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}
+    assert list(dsd.keys()) == list(dec.state_dict().keys())          # same keys in the same registration order
+    dec.load_state_dict(dsd, strict=True)
+    pq = torch.nn.Conv2d(4, 4, 1)
+    pq.load_state_dict({"weight": sd["post_quant_conv.weight"], "bias": sd["post_quant_conv.bias"]})
+    g = torch.Generator().manual_seed(31)
+    z = torch.randn(2, 4, 8, 8, generator=g) * 0.18215 * 4.0
+    with torch.no_grad():
+        img = dec(pq((1.0 / 0.18215) * z))                               # FrozenAutoencoderKL.decode, :449-453
+        u8 = img.clone().add_(1).mul(127.5).clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1)   # sample.py:287
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), z=z.numpy(), images=img.numpy(), u8=u8.numpy())
+    print(name, "image range", img.min().item(), img.max().item(), "mean |img|", img.abs().mean().item())
+
+
 def round2_cases():
     """Round 2: goldens that reach the PRODUCTION kernels: XL/2 at R=32 has T=128 kept tokens,
     so B=2 gives M=256 token rows (2-CTA GEMM tiles) and the split-tile tcgen05 attention forward/backward
@@ -276,6 +302,7 @@ def round2_cases():
 
 
 def round2_small():
+    vae_case("vae_decode")
     front_case("step_front")
     ablation_case("s2_ablation", O.Cfg(model_type="DiT-S/2", img_resolution=8, num_classes=10), B=2)
 

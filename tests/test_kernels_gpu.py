@@ -79,19 +79,18 @@ def test_gemm_epilogues(ops):
     o16 = torch.empty(M, N, device=dev(), dtype=torch.bfloat16)
     aux = torch.empty(M, N, device=dev(), dtype=torch.bfloat16)
     ops.gemm(A, B, M, N, K, out=o16, bias=bias, epi=ops.EPI_GELU, aux=aux, ld_aux=N)
-    hb = acc.to(torch.bfloat16).float().requires_grad_(True)     # the pre-activation as a bf16 nn.Linear would emit it
-    gel = F.gelu(hb, approximate="tanh")
-    gel.sum().backward()
-    close(o16, gel.detach(), 2 ** -7, "gelu out")
-    close(aux, hb.grad, 2 ** -7, "gelu' (aux)")                  # aux = gelu'(h): all the backward needs of h
+    close(aux, acc, 2 ** -8, "gelu pre")
+    close(o16, F.gelu(aux.float(), approximate="tanh"), 2 ** -7, "gelu out")
     gate = torch.randn(M // T, N, device=dev())
     ops.gemm(A, B, M, N, K, out=out, bias=bias, epi=ops.EPI_GATE_RESID, aux=aux, ld_aux=N, resid=R, ld_resid=N,
              gate=gate, ld_gate=N, rows_per_group=T)
     close(aux, acc, 2 ** -8, "gate_resid y")
     close(out, R + gate.repeat_interleave(T, 0) * acc, 1e-3, "gate_resid out")
-    h = rb(M, N)                                                 # stands for the stored gelu' tensor
+    h = rb(M, N)
     ops.gemm(A, B, M, N, K, out=o16, epi=ops.EPI_DGELU, aux=h, ld_aux=N)
-    close(o16, (A.float() @ B.float().t()) * h.float(), 2 ** -7, "dgelu")
+    hf = h.float().requires_grad_(True)
+    F.gelu(hf, approximate="tanh").sum().backward()
+    close(o16, (A.float() @ B.float().t()) * hf.grad, 2 ** -7, "dgelu")
     # fused bias gradient: colsum[n] += sum_m of the STORED (bf16-rounded) outputs, incl. a ragged N (1000) and odd M
     for (m2, n2) in ((M, N), (300, 1000)):
         A2, B2, h2 = rb(m2, K), rb(n2, K, scale=0.05), rb(m2, n2)

@@ -307,7 +307,7 @@ def test_optimizer_state_layouts_and_namespace_checkpoint(tmp_path):
 def test_c_driver_matches_python_engine(case):
     """`mdt_forward` (one ctypes call, one workspace) == `Engine.forward` (per-kernel ctypes calls) BIT FOR BIT: same
     kernels, same order, same operands.  The backward accumulates wgrads with fp32 atomics (run-to-run order noise), so
-    gradients are compared at 5e-4 of each tensor's scale."""
+    gradients are compared at 5e-5 of each tensor's scale (1e-2 on the conditioning path, see below)."""
     from maskdit_b200.engine import CEngine, Engine
     g = load(case)
     xl = case.startswith("xl2")
@@ -338,9 +338,12 @@ def test_c_driver_matches_python_engine(case):
         a, b = gc[o:o + n], gp[o:o + n]
         err = (a - b).abs().max().item() / (b.abs().max().item() + 1e-30)
         worst = max(worst, err)
-        # order noise of the fp32 atomics (1e-7 .. 1e-5), amplified where a value is re-rounded to bf16 before the next
-        # GEMM (dmod -> bf16 -> adaLN wgrad over only B rows: measured up to 1.1e-4) - not a code difference
-        assert err <= 5e-4, (k, err)
+        # Order noise of the fp32 atomics: 1e-7 .. 1e-5 on the block tensors.  On the conditioning path the noisy sums
+        # are re-rounded to bf16 several times before GEMMs that contract over only B = 2 rows (dmod -> bf16 -> adaLN
+        # wgrad; dsc -> dc (bf16) -> dth -> dpre (bf16) -> t_embedder wgrad): one flipped bf16 rounding moves an element
+        # by 2^-8, measured up to 2e-3 of a tensor's scale between two runs of the SAME engine - not a code difference.
+        cond = any(t in k for t in ("adaLN_modulation", "t_embedder", "y_embedder"))
+        assert err <= (1e-2 if cond else 5e-5), (k, err)
     print(case, "C driver vs Python engine: forward bit-equal, worst gradient deviation", worst)
     # the workspace contract: mdt_workspace_bytes is what mdt_forward checks against
     B, T = x.shape[0], (md["ids_keep"].shape[1] if md else cfg.num_patches)
@@ -352,3 +355,31 @@ def test_c_driver_matches_python_engine(case):
         ops_.check(ce._L.mdt_forward(ce._h, st.w32.data_ptr(), st.w16.data_ptr(), x.data_ptr(), sigma.data_ptr(),
                                      lab.data_ptr(), 0, 0, B, 0, 0, small.data_ptr(), 1024, Fc.data_ptr(),
                                      torch.cuda.current_stream().cuda_stream), "mdt_forward", 0)
+
+
+# ---- round 2: the sampler tail — SD-VAE decode on the tcgen05 GEMM + fused im2col (sample.py:275,287) ----------------
+def test_vae_decode_vs_reference_golden():
+    """`AutoencoderKLDecoder.decode` vs the unmodified reference Decoder + post_quant_conv (autoencoder.py:306-453) on the
+    stand-in weights: 8x8 latents -> 64x64 images (every layer type: conv_in, ResnetBlocks with and without nin_shortcut,
+    the AttnBlock, three upsampling convolutions, norm_out + conv_out), then the 8-bit conversion of sample.py:287."""
+    from maskdit_b200 import ops
+    from maskdit_b200.vae import AutoencoderKLDecoder
+    from oracle import vae_oracle as VO
+    g = load("vae_decode")
+    vae = AutoencoderKLDecoder()
+    vae.load_state_dict(VO.make_vae_state_dict(3), strict=True)
+    vae = vae.cuda().eval()
+    img = vae.decode(g["z"].cuda())
+    assert img.shape == g["images"].shape and torch.isfinite(img).all()
+    r = rel_l2(img, g["images"])
+    print("VAE decode rel-L2 vs the reference's fp32 output:", r)
+    assert r <= 2e-2, r                                   # ~30 bf16-operand convolutions, re-normalised by GroupNorm
+    u8 = ops.to_uint8_nhwc(img.contiguous()).cpu()
+    diff = (u8.int() - g["u8"].int()).abs()
+    print("8-bit image: mean |diff|", diff.float().mean().item(), "max", diff.max().item())
+    assert diff.float().mean().item() <= 1.5
+    # chunked im2col (several GEMM launches per convolution) gives the same image bit for bit
+    vae.max_rows = 2048
+    assert torch.equal(vae.decode(g["z"].cuda()), img)
+    with pytest.raises(NotImplementedError):
+        vae(g["z"].cuda(), "encode")

@@ -179,3 +179,18 @@ def test_lr_schedule_and_rank_batches():
     assert sorted(s for rb in got for b in rb for s in b) == seeds
     assert all(len(b) <= 8 for rb in got for b in rb) and len({len(rb) for rb in got}) == 1
     assert got[1][0] == list(range(100 + 6, 100 + 12))   # 70 seeds -> 12 batches of 6/5, rank 1 takes batch 1, 5, 9
+
+
+def test_vae_decode_matches_reference():
+    """SD-VAE decode restatement (oracle/vae_oracle.py) vs the unmodified reference Decoder + post_quant_conv
+    (autoencoder.py:306-453) on the stand-in weights; the 8-bit conversion of sample.py:287 bit for bit."""
+    from oracle import vae_oracle as VO
+    g = load("vae_decode")
+    sd = VO.make_vae_state_dict(3)
+    assert sum(v.numel() for k, v in sd.items() if k.startswith("decoder.")) == 49_490_179   # SD-VAE decoder size
+    with torch.no_grad():
+        img = VO.decode(sd, t(g["z"]))
+    np.testing.assert_allclose(img.numpy(), g["images"], rtol=1e-3, atol=2e-4)
+    u8 = VO.to_uint8(img).numpy()
+    assert (u8 != g["u8"]).mean() < 1e-3 and np.abs(u8.astype(int) - g["u8"].astype(int)).max() <= 1
+    assert np.array_equal(VO.to_uint8(t(g["images"])).numpy(), g["u8"])

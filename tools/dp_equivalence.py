@@ -57,7 +57,8 @@ def main():
 
     # single-GPU gradient of the whole global batch (every rank computes it locally: same weights, same draws)
     ref_net = copy.deepcopy(base).to(dev).train()
-    ts_ref = TrainStep(ref_net, None, lr=1e-3, loss_fn=Draws(rnd, noise, mnoise, 0, Bg), process_group=None)
+    ts_ref = TrainStep(ref_net, None, lr=1e-3, loss_fn=Draws(rnd, noise, mnoise, 0, Bg), process_group=None,
+                       grad_dtype="fp32")
     ts_ref.world, ts_ref.comm, ts_ref.g16 = 1, None, None      # a 1-GPU step inside the N-rank job
     ts_ref._grad_scale = 1.0
     ts_ref.step(images, labels, 0.5, 0.1)

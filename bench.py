@@ -176,8 +176,68 @@ def cpu_reference_eval(R=32):
     return fwd, B / (35 * per_eval)
 
 
-def cpu_baseline_record(steps, warmup, R=32, B=8, extras=False):
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def have_unmodified_reference():
+    return os.path.exists(os.path.join(REF_DIR, "models", "maskdit.py"))
+
+
+def cpu_reference_train_unmodified(B, steps, warmup, R=32):
+    """The UNMODIFIED reference (`models/maskdit.py` + `train_utils/loss.py`, staged from /root/reference into the
+    git-ignored baseline/_ref/ by `__graft_entry__.build()`), imported through the timm stand-in, fp32, PyTorch CPU backend,
+    `torch.optim.AdamW(weight_decay=0)` in place of apex FusedAdam, the net wrapped to expose `.module` as the loss
+    expects (loss.py:47) - BASELINE.md section 3.  Zero-initialised tensors randomised N(0, 0.02) like the GPU run."""
+    from oracle import timm_standin
+    timm_standin.install()
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import models.maskdit as rm
+    import train_utils.loss as rl
+    torch.manual_seed(0)
+    net = rm.Precond_models["edm"](img_resolution=R, img_channels=4, num_classes=1000, model_type="DiT-XL/2",
+                                   use_decoder=True, mae_loss_coef=0.1, pad_cls_token=False).train()
+    randomise_zero_init(net)
+
+    class Wrap:
+        def __init__(self, m):
+            self.module, self.model, self.training = m, m.model, True
+
+        def __call__(self, *a, **k):
+            return self.module(*a, **k)
+
+    wrap, loss_fn = Wrap(net), rl.Losses["edm"]()
+    opt = torch.optim.AdamW([p for p in net.parameters() if p.requires_grad], lr=1e-4, weight_decay=0)
+    g = torch.Generator().manual_seed(0)
+    times = []
+    for it in range(warmup + steps):
+        x = torch.randn(B, 4, R, R, generator=g) * 0.5
+        y = torch.nn.functional.one_hot(torch.randint(0, 1000, (B,), generator=g), 1000).float()
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = loss_fn(net=wrap, images=x, labels=y, mask_ratio=0.5, mae_loss_coef=0.1)
+        loss.mean().backward()
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return B * len(times) / sum(times), sum(times)
+
+
+def cpu_baseline_record(steps, warmup, R=32, B=8, extras=False, prefer_unmodified=False):
     threads, how = pin_to_one_socket()
+    if prefer_unmodified and have_unmodified_reference():
+        sps, secs = cpu_reference_train_unmodified(B, steps, warmup, R=R)
+        extra = {}
+        if extras:
+            fwd, ips = cpu_reference_eval(R)
+            extra = {"c1_forward_b2": {"value": fwd, "unit": "samples/s", "kind": "port"},
+                     "c5_sampler_b2_scaled": {"value": ips, "unit": "img/s", "kind": "port",
+                                              "how": "3 CFG network evaluations at B=2 timed, scaled to the 35 of an 18-step run"}}
+        return sps, secs, {**extra, "value": sps, "unit": "samples/s", "cores": threads, "kind": "reference", "same_config": False,
+                           "sample": f"{steps} timed steps (+{warmup} warm-up) of batch {B} (SURVEY 8d): the UNMODIFIED "
+                                     f"reference modules (models/maskdit.py + train_utils/loss.py staged in baseline/_ref, "
+                                     f"timm stand-in), EDM loss fwd + bwd + torch AdamW(wd=0), torch CPU fp32, {threads} "
+                                     f"threads {how}; host has {os.cpu_count()} logical CPUs; {secs:.1f} s timed"}
     sps, secs = cpu_reference_train(B, steps, warmup, R=R)
     extra = {}
     if extras:
@@ -197,7 +257,7 @@ def run_reference_arm(args, rank):
         return
     R = 64 if args.workload == "train512" else 32
     B = 8 if R == 32 else 2
-    sps, secs, rec = cpu_baseline_record(args.steps, max(1, min(args.warmup, 2)), R=R, B=B)
+    sps, secs, rec = cpu_baseline_record(args.steps, max(1, min(args.warmup, 2)), R=R, B=B, prefer_unmodified=True)
     line = {"impl": "reference", "metric": "train_samples_per_sec", "value": sps, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -321,7 +381,8 @@ def main():
             del os.environ["MDT_GRAD_AR"], net2
             torch.cuda.empty_cache()
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            _, _, line["cpu_baseline"] = cpu_baseline_record(3, 1, R=R, B=8 if R == 32 else 2, extras=(R == 32))
+            _, _, line["cpu_baseline"] = cpu_baseline_record(3, 1, R=R, B=8 if R == 32 else 2, extras=(R == 32),
+                                                             prefer_unmodified=True)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

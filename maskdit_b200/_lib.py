@@ -99,7 +99,7 @@ _SIGS = {
     "mdt_nccl_comm_destroy": [_P],
     "mdt_allreduce_grads": [_P, _P, _LL, _I, _P],
     "mdt_vae_post_quant": [_P, _P, _P, _F, _P, _I, _I, _I, _P],
-    "mdt_vae_gn_stats": [_P, _P, _I, _I, _I, _P],
+    "mdt_vae_gn_stats": [_P, _P, _P, _I, _I, _I, _P],
     "mdt_vae_im2col": [_P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P],
     "mdt_vae_softmax_rows": [_P, _F, _P, _I, _I, _P],
     "mdt_vae_rows_to_nchw": [_P, _P, _I, _I, _I, _I, _P],

@@ -34,16 +34,16 @@ __global__ void vae_post_quant_kernel(const float* __restrict__ z, const float* 
   }
 }
 
-// GroupNorm(32) statistics of x [B, P, C] f32: sums[b][g] = (sum, sum of squares) in fp64 (caller zeroes `sums`).
-// Thread = 4 channels of one pixel lane; block = C/4 x (256 / (C/4)) threads over kGnPix pixels.
+// GroupNorm(32) statistics of x [B, P, C] f32, DETERMINISTIC (no atomics: with bf16 GEMM operands downstream, 1e-7
+// order noise in a mean flips bf16 roundings and shows up as 4e-3 run-to-run differences in the decoded image, measured):
+//   pass 1: block (b, chunk of kGnPix pixels) -> partial[b][chunk][g] = (sum, sum of squares) fp32, fixed-order tree
+//   pass 2: sums[b][g] = fixed-order fp64 sum of the partials.
+// Thread = 4 channels of one pixel lane; block = C/4 x (256 / (C/4)) threads: always 8 threads per group.
 constexpr int kGnPix = 256;
 __global__ void __launch_bounds__(256)
-vae_gn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, int P, int C) {
-  __shared__ float s_acc[32][2];
+vae_gn_partial_kernel(const float* __restrict__ x, float* __restrict__ partial, int P, int C) {
+  __shared__ float s_part[256][2];
   const int tx = threadIdx.x, ty = threadIdx.y, b = blockIdx.y;
-  const int tid = ty * blockDim.x + tx;
-  if (tid < 64) (&s_acc[0][0])[tid] = 0.f;
-  __syncthreads();
   const int p0 = blockIdx.x * kGnPix;
   float s = 0.f, ss = 0.f;
   for (int p = p0 + ty; p < min(P, p0 + kGnPix); p += blockDim.y) {
@@ -51,14 +51,26 @@ vae_gn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, int 
     s += (v.x + v.y) + (v.z + v.w);
     ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
   }
-  const int g = (4 * tx) / (C / 32);
-  atomicAdd(&s_acc[g][0], s);
-  atomicAdd(&s_acc[g][1], ss);
+  // slot = (group, member): the 8 threads of a group occupy 8 consecutive slots
+  const int tpg = (C / 32) / 4;                       // threads per group along x (1, 2 or 4)
+  const int g = tx / tpg, member = ty * tpg + (tx - g * tpg);
+  s_part[g * 8 + member][0] = s;
+  s_part[g * 8 + member][1] = ss;
   __syncthreads();
-  if (tid < 32) {
-    atomicAdd(&sums[(static_cast<long long>(b) * 32 + tid) * 2 + 0], static_cast<double>(s_acc[tid][0]));
-    atomicAdd(&sums[(static_cast<long long>(b) * 32 + tid) * 2 + 1], static_cast<double>(s_acc[tid][1]));
+  const int tid = ty * blockDim.x + tx;
+  if (tid < 64) {
+    const int gg = tid >> 1, w = tid & 1;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += s_part[gg * 8 + k][w];
+    partial[((static_cast<long long>(b) * gridDim.x + blockIdx.x) * 32 + gg) * 2 + w] = acc;
   }
+}
+__global__ void vae_gn_finish_kernel(const float* __restrict__ partial, double* __restrict__ sums, int nchunk) {
+  const int b = blockIdx.x, t = threadIdx.x;  // 64 threads: (group, which)
+  double acc = 0.0;
+  for (int k = 0; k < nchunk; ++k) acc += static_cast<double>(partial[(static_cast<long long>(b) * nchunk + k) * 64 + t]);
+  sums[static_cast<long long>(b) * 64 + t] = acc;
 }
 
 // im2col with the producer fused in:  A[(b, y, x), (ky, kx, c)] = f(src[b, (y+ky-pad)/up, (x+kx-pad)/up, c])  (0 outside)
@@ -157,13 +169,13 @@ int mdt_vae_post_quant(const float* z, const float* W, const float* bias, float 
   return vae_status();
 }
 
-int mdt_vae_gn_stats(const float* x, double* sums, int B, int P, int C, void* stream) {
-  if (!x || !sums || B <= 0 || P <= 0 || C % 128 || C > 1024) return MDT_ERR_ARG;  // C/32 channels per group, >= 4
+int mdt_vae_gn_stats(const float* x, double* sums, float* scratch, int B, int P, int C, void* stream) {
+  if (!x || !sums || !scratch || B <= 0 || P <= 0 || C % 128 || C > 512) return MDT_ERR_ARG;  // 4..16 channels / group
   if (reinterpret_cast<uintptr_t>(x) & 15) return MDT_ERR_ARG;
-  if (cudaMemsetAsync(sums, 0, static_cast<size_t>(B) * 32 * 2 * sizeof(double), VS(stream)) != cudaSuccess)
-    return MDT_ERR_CUDA;
-  dim3 block(C / 4, 256 / (C / 4)), grid((P + kGnPix - 1) / kGnPix, B);
-  vae_gn_stats_kernel<<<grid, block, 0, VS(stream)>>>(x, sums, P, C);
+  const int nchunk = (P + kGnPix - 1) / kGnPix;
+  dim3 block(C / 4, 256 / (C / 4)), grid(nchunk, B);
+  vae_gn_partial_kernel<<<grid, block, 0, VS(stream)>>>(x, scratch, P, C);
+  vae_gn_finish_kernel<<<B, 64, 0, VS(stream)>>>(scratch, sums, nchunk);
   return vae_status();
 }
 

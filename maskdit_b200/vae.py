@@ -124,9 +124,7 @@ class AutoencoderKLDecoder(nn.Module):
         out = torch.empty(M, ldo, dtype=f32, device=x.device)
         sums = gamma = beta = None
         if norm is not None:
-            sums = torch.empty(B, 32, 2, dtype=torch.float64, device=x.device)
-            ops.check(ops.lib().mdt_vae_gn_stats(ops.ptr(x), ops.ptr(sums), B, (H // up) * (W // up), cin,
-                                                 ops.stream_ptr()), "mdt_vae_gn_stats")
+            sums = self._gn_stats(x, B, (H // up) * (W // up), cin)
             gamma, beta = self._packed[f"{norm}.weight"], self._packed[f"{norm}.bias"]
         per = max(1, min(B, self.max_rows // (H * W)))        # images per im2col operand
         A = torch.empty(per * H * W, Kp, dtype=bf16, device=x.device)
@@ -142,6 +140,14 @@ class AutoencoderKLDecoder(nn.Module):
                      resid=resid[b0 * H * W:] if resid is not None else None, ld_resid=cout)
         return out   # (ldo > cout only for conv_out: the caller reads the first cout columns)
 
+    def _gn_stats(self, x, B, P, C):
+        """GroupNorm(32) sums [B,32,2] f64 of x [B*P, C] (deterministic two-pass reduction: decode is run-to-run stable)."""
+        sums = torch.empty(B, 32, 2, dtype=torch.float64, device=x.device)
+        scratch = torch.empty(B * ((P + 255) // 256) * 64, dtype=f32, device=x.device)
+        ops.check(ops.lib().mdt_vae_gn_stats(ops.ptr(x), ops.ptr(sums), ops.ptr(scratch), B, P, C, ops.stream_ptr()),
+                  "mdt_vae_gn_stats", 2)
+        return sums
+
     def _resblock(self, x, B, H, W, name, cin, cout):
         """ResnetBlock.forward with temb = None (autoencoder.py:117-137)."""
         h = self._conv(x, B, H, W, cin, f"{name}.conv1", norm=f"{name}.norm1", silu=True)
@@ -155,8 +161,7 @@ class AutoencoderKLDecoder(nn.Module):
         T, M = H * W, B * H * W
         dev = x.device
         q, k, v = (torch.empty(M, c, dtype=bf16, device=dev) for _ in range(3))
-        sums = torch.empty(B, 32, 2, dtype=torch.float64, device=dev)
-        ops.check(ops.lib().mdt_vae_gn_stats(ops.ptr(x), ops.ptr(sums), B, T, c, ops.stream_ptr()), "mdt_vae_gn_stats")
+        sums = self._gn_stats(x, B, T, c)
         xn = torch.empty(M, c, dtype=bf16, device=dev)
         ops.check(ops.lib().mdt_vae_im2col(ops.ptr(x), ops.ptr(sums), ops.ptr(self._packed[f"{name}.norm.weight"]),
                                            ops.ptr(self._packed[f"{name}.norm.bias"]), 0, 1, 1, ops.ptr(xn), B, H, W, c,

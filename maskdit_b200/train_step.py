@@ -152,10 +152,15 @@ class TrainStep:
         assert self.collective in ("mdt", "torch") and self.grad_dtype in ("fp32", "bf16")
         self.comm_ctas = int(env.get("MDT_COMM_CTAS", comm_ctas if comm_ctas is not None else 8))
         self.comm = None
+        self.comm_bg = None
         self.g16 = None
         if self.world > 1:
             if self.collective == "mdt":
-                self.comm = GradComm(process_group, max_ctas=max(1, self.comm_ctas // 2) if self.overlap else 0)
+                self.comm = GradComm(process_group)               # full-width communicator (NVLS, all channels)
+                # a second communicator confined to a few CTAs carries the per-block chunks DURING the backward; the
+                # gradients that only become final at its very end (adaLN projections = 35 % of the volume, embeddings)
+                # go through the full-width one afterwards
+                self.comm_bg = GradComm(process_group, max_ctas=max(1, self.comm_ctas // 2)) if self.overlap else None
             if self.grad_dtype == "bf16":
                 self.g16 = torch.empty(n, dtype=torch.bfloat16, device=dev)
         self._sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -232,9 +237,10 @@ class TrainStep:
 
     def close(self):
         """Release the communicator (a TrainStep owns one when world > 1 and collective == 'mdt')."""
-        if self.comm is not None:
-            self.comm.close()
-            self.comm = None
+        for c in (self.comm, self.comm_bg):
+            if c is not None:
+                c.close()
+        self.comm = self.comm_bg = None
         self.net._grad_ready_hook = None
 
     # -- gradient exchange + optimizer ------------------------------------------------------------------------------------
@@ -248,7 +254,7 @@ class TrainStep:
             if self.ar_chunks > 1 else "one flat call after the backward")
         return f"{self.grad_dtype} sum-all-reduce of the flat gradient buffer, {how}, {when}"
 
-    def _exchange(self, lo, hi):
+    def _exchange(self, lo, hi, background=False):
         """Sum gradient elements [lo, hi) over the ranks on the current stream (in `grad`, or in the bf16 buffer)."""
         if hi <= lo or self.world == 1:
             return
@@ -257,7 +263,7 @@ class TrainStep:
         if self.g16 is not None:
             buf = ops.cast_bf16(buf, out=self.g16[lo:hi])
         if self.comm is not None:
-            self.comm.all_reduce(buf)
+            (self.comm_bg if (background and self.comm_bg is not None) else self.comm).all_reduce(buf)
         else:
             dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)
 
@@ -279,7 +285,7 @@ class TrainStep:
         main = torch.cuda.current_stream()
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
-            self._exchange(lo, hi)
+            self._exchange(lo, hi, background=True)
         self._done.append((lo, hi))
 
     def _fwd_bwd_graphed(self, images, labels, mask_ratio, mae_loss_coef, loss_call, moments=False):

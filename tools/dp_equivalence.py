@@ -91,8 +91,7 @@ def main():
                   f"[{ts.describe_collective()}]", flush=True)
         assert r <= tol, (name, r)
         assert dw <= 2.5e-3, (name, dw)      # one Adam step of lr 1e-3: sign-like, order noise flips only ~0 gradients
-        if ts.comm is not None:
-            ts.comm.close()
+        ts.close()
     dist.barrier()
     if rank == 0:
         print("DP_EQUIV_OK", flush=True)

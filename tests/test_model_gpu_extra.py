@@ -373,7 +373,7 @@ def test_vae_decode_vs_reference_golden():
     assert img.shape == g["images"].shape and torch.isfinite(img).all()
     r = rel_l2(img, g["images"])
     print("VAE decode rel-L2 vs the reference's fp32 output:", r)
-    assert r <= 2e-2, r                                   # ~30 bf16-operand convolutions, re-normalised by GroupNorm
+    assert r <= 1e-2, r                                   # measured 5.5e-3: ~30 bf16-operand convolutions
     u8 = ops.to_uint8_nhwc(img.contiguous()).cpu()
     diff = (u8.int() - g["u8"].int()).abs()
     print("8-bit image: mean |diff|", diff.float().mean().item(), "max", diff.max().item())

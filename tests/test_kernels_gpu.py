@@ -433,3 +433,26 @@ def test_sampler_tail_uint8_and_lincomb(ops):
     assert torch.allclose(out, want, rtol=1e-14, atol=1e-14) and torch.allclose(o32, (want * 0.5).float(), rtol=1e-6)
     ops.lincomb_f64(2.0, x, out=x)                                   # in place, x only
     assert torch.allclose(x, want * 0 + x)                           # finite, no aliasing fault
+
+
+def test_attention_strict_mode_refuses_the_mma_sync_fallback():
+    """MDT_ATTN_STRICT=1: a shape no tcgen05 kernel accepts (T = 200) is an error instead of a silent mma.sync run; the
+    production shapes are unaffected.  (The switch is read once per process: checked in a child process.)"""
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from maskdit_b200 import ops\n"
+        "from maskdit_b200._lib import MdtError\n"
+        "q = torch.randn(2 * 128, 3 * 16 * 72, device='cuda').to(torch.bfloat16)\n"
+        "ops.attention_fwd(q, 2, 128, 16, 72)\n"
+        "assert ops.lib().mdt_attention_last_impl(0) == 1\n"
+        "q = torch.randn(200, 3 * 4 * 72, device='cuda').to(torch.bfloat16)\n"
+        "try:\n"
+        "    ops.attention_fwd(q, 1, 200, 4, 72)\n"
+        "    print('NO_ERROR')\n"
+        "except MdtError as e:\n"
+        "    print('STRICT_OK', e)\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MDT_ATTN_STRICT="1"), capture_output=True,
+                       text=True, timeout=300)
+    assert "STRICT_OK" in r.stdout and "unsupported" in r.stdout, r.stdout + r.stderr

@@ -447,21 +447,21 @@ def bench_train(args, net, env, R, PK, B, steps, warmup, full):
     ms_e2e = env.timed(step_e2e, steps)
     final_loss = float(loss_host.item())
 
-    # dominant kernel (the tcgen05 GEMM family) timed per launch with CUDA events inside one real step
-    # (the C++ step driver issues the GEMMs itself, so this ONE extra step runs the identical launch sequence through the
-    # kernel-by-kernel Python engine, whose gemm() wrapper brackets every launch with events on the launching stream)
-    from maskdit_b200.engine import Engine
-    c_engine, net._engine = net._engine, Engine(net._cfg(), net.flat_store())
-    # three such steps; per launch the MEDIAN of the three (an event pair also spans any bubble in which the GPU waits for
-    # this Python-paced enqueue, which is not kernel time: one step alone gave 0.745 .. 0.81 on identical code)
+    # dominant kernel (the tcgen05 GEMM family) timed per launch with CUDA events inside real steps: the library brackets
+    # every mdt_gemm_bf16 launch - the C++ step driver's own - with an event pair on the launching stream
+    # (mdt_gemm_profile_enable); three steps, per launch the median of the three.
+    import ctypes
+    L = _lib.lib()
     runs = []
     for i in range(3):
-        _lib.GEMM_PROFILE = []
+        L.mdt_gemm_profile_enable(1)
         step_resident(i)
         torch.cuda.synchronize()
-        runs.append([(f, a.elapsed_time(b)) for f, a, b, _k in _lib.GEMM_PROFILE])
-    _lib.GEMM_PROFILE = None
-    net._engine = c_engine
+        L.mdt_gemm_profile_enable(0)
+        n = L.mdt_gemm_profile_read(None, None, 0)
+        ms_buf, fl_buf = (ctypes.c_float * n)(), (ctypes.c_double * n)()
+        assert L.mdt_gemm_profile_read(ms_buf, fl_buf, n) == n
+        runs.append(list(zip(list(fl_buf), list(ms_buf))))
     prof = runs[0]
     assert all(len(r) == len(prof) for r in runs)
     gemm_ms = sum(sorted(r[j][1] for r in runs)[1] for j in range(len(prof)))

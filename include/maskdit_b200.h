@@ -73,6 +73,11 @@ typedef struct mdt_gemm_args {
 } mdt_gemm_args;
 
 int mdt_gemm_bf16(const mdt_gemm_args* args, void* stream);
+/* Measurement aid (bench.py roofline): while enabled, every mdt_gemm_bf16 launch of this process - also the step
+ * driver's - is bracketed by CUDA events on its stream; mdt_gemm_profile_read returns the launch count and fills
+ * ms[i] (device time) / flops[i] (2 M N K) for i < cap.  Enabling clears the previous recording.                   */
+int mdt_gemm_profile_enable(int on);
+int mdt_gemm_profile_read(float* ms, double* flops, int cap);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Mask index path (integer, bit-exact).  get_mask, models/maskdit.py:88-113: ids_shuffle = argsort(noise),

@@ -58,6 +58,8 @@ _lib = None
 _P, _I, _F, _LL, _D = c_void_p, c_int, c_float, c_longlong, c_double
 _SIGS = {
     "mdt_gemm_bf16": [POINTER(GemmArgs), _P],
+    "mdt_gemm_profile_enable": [_I],
+    "mdt_gemm_profile_read": [_P, _P, _I],
     "mdt_mask_indices": [_P, _I, _I, _I, _P, _P, _P, _P],
     "mdt_patch_embed": [_P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "mdt_patch_embed_bwd": [_P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

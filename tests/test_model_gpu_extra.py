@@ -385,3 +385,23 @@ def test_vae_decode_vs_reference_golden():
     assert torch.equal(vae.decode(g["z"].cuda()), img)
     with pytest.raises(NotImplementedError):
         vae(g["z"].cuda(), "encode")
+
+
+def test_unconditional_odd_token_count_vs_reference_golden():
+    """Edge geometry against the unmodified reference: class-UNconditional network (num_classes = 0: no label embedder,
+    labels None) with 30 % masking -> 179 kept tokens per sample, batch 3: token counts that are not multiples of 128
+    (the mma.sync attention kernels, asserted), ragged GEMM M (537 / 768 rows), loss and every gradient."""
+    g = load("s2_uncond_mask30")
+    net, cfg, _ = build("DiT-S/2", 32, 0)
+    net.train()
+    lf = GoldenLoss(g)
+    with ImplRecorder() as rec:
+        loss = lf(net, g["images"].cuda(), None, mask_ratio=0.3, mae_loss_coef=0.1)
+        for k in ("mask", "ids_keep", "ids_restore"):
+            assert torch.equal(lf.last_mask_dict[k].cpu(), g[k]), k
+        loss.mean().backward()
+    assert lf.last_mask_dict["ids_keep"].shape == (3, 179)
+    assert torch.allclose(loss.cpu(), g["loss"], rtol=LOSS_TOL), (loss, g["loss"])
+    check_grads(net, g, what="unconditional, T=179")
+    assert (179, 64, 0) in rec.attn_fwd and (179, 64, 0) in rec.attn_bwd, (rec.attn_fwd, rec.attn_bwd)
+    assert (256, 32, 1) in rec.attn_fwd            # the decoder still runs all 256 tokens on the tcgen05 kernels

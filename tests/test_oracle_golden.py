@@ -42,7 +42,8 @@ XL64 = O.Cfg(model_type="DiT-XL/2", img_resolution=64, num_classes=1000)
 
 
 @pytest.mark.parametrize("name,CFG", [("s2_train_mask", SMALL), ("s2_train_nomask", SMALL), ("b4_train_mask75", B4),
-                                      ("xl2_c1_grads", XL32), ("xl2_r64_grads", XL64)])
+                                      ("xl2_c1_grads", XL32), ("xl2_r64_grads", XL64),
+                                      ("s2_uncond_mask30", O.Cfg(model_type="DiT-S/2", img_resolution=32, num_classes=0))])
 def test_train_loss_and_grads_match_reference(name, CFG):
     g = load(name)
     SMALL = CFG  # noqa: N806 - the body below is written against the small config's name
@@ -52,7 +53,8 @@ def test_train_loss_and_grads_match_reference(name, CFG):
     if md is not None:
         for k in ("mask", "ids_keep", "ids_restore"):
             assert np.array_equal(md[k].numpy(), g[k])
-    loss, D = O.edm_loss(sd, SMALL, t(g["images"]), t(g["labels"]), t(g["rnd_normal"]), t(g["noise_unit"]), md,
+    labels = t(g["labels"]) if "labels" in g else None           # class-unconditional golden: labels None
+    loss, D = O.edm_loss(sd, SMALL, t(g["images"]), labels, t(g["rnd_normal"]), t(g["noise_unit"]), md,
                          SMALL.mae_loss_coef)
     np.testing.assert_allclose(loss.detach().numpy(), g["loss"], rtol=2e-5, atol=1e-6)
     np.testing.assert_allclose(D.detach().numpy(), g["D"], rtol=1e-4, atol=2e-5)

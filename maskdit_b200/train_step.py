@@ -116,7 +116,8 @@ class TrainStep:
                       'fp32': the 2.92 GB buffer is reduced as is (DDP's arithmetic; rel-L2 1e-5, order noise).
           overlap     the exchange of a block's gradients starts as soon as its backward is enqueued, on a side stream,
                       through a communicator confined to `comm_ctas` CTAs while the persistent GEMM / attention grids
-                      are sized for (SMs - comm_ctas) (`mdt_set_sm_budget`): the transfer hides behind the backward.
+                      are sized for (SMs - comm_ctas) (`mdt_set_sm_budget`).  Measured SLOWER than the default on B200
+                      (133.1 vs 130.2 ms at 2 GPUs, profiles/r02_experiments.md section 5): off by default, kept for A/B.
         Environment overrides: MDT_COLLECTIVE, MDT_GRAD_AR, MDT_OVERLAP, MDT_COMM_CTAS."""
         self.net, self.ema = net, ema
         self.lr, self.betas, self.eps, self.wd, self.ema_decay = lr, betas, eps, weight_decay, ema_decay

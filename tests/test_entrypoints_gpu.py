@@ -83,3 +83,19 @@ def test_train_from_lmdb_dataset_with_grad_accum_then_resume_and_ablation_genera
     z = np.load(tmp_path / "samples" / "000001.npy")
     assert z.shape == (4, 16, 16) and np.isfinite(z).all()
     assert open(tmp_path / "samples" / "000001.png", "rb").read(8) == b"\x89PNG\r\n\x1a\n"
+
+
+def test_train_from_webdataset_shards(tmp_path):
+    """train.py --wds: the reference's WebDataset layout (lmdb2wds.py:26) feeds the same fused step front."""
+    sys.path.insert(0, ROOT)
+    from maskdit_b200.data import write_wds_shard
+    rng = np.random.default_rng(1)
+    os.makedirs(tmp_path / "shards")
+    for s in range(2):
+        write_wds_shard(str(tmp_path / "shards" / f"latent-{s:04d}.tar"),
+                        rng.standard_normal((24, 8, 16, 16)).astype(np.float32), rng.integers(0, 1000, 24), start=24 * s)
+    cfg = tmp_path / "cfg.yaml"
+    cfg.write_text(YAML.replace("root: none", f"root: {tmp_path / 'shards'}"))
+    out = run([os.path.join(ROOT, "train.py"), "--config", str(cfg), "--wds", "--max_steps", "4", "--results_dir",
+               str(tmp_path / "res")], str(tmp_path))
+    assert "2 WebDataset shards" in out and "(step=0000004)" in out

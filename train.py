@@ -10,7 +10,8 @@ is one precision recipe); the DDP wrapper + apex FusedAdam + EMA loop are replac
 all-reduce, fused AdamW+EMA); wandb / FID-during-training are not wired (out of scope).
 Data: the reference's LMDB latent dataset (`data.root`/train: keys z-{i} / y-{i} / length, train_utils/datasets.py:
 240-304) through `maskdit_b200.data` (liblmdb when the `lmdb` module exists, otherwise a read-only page walker of
-data.mdb); `--synthetic` draws VAE moments of the configured shape instead (no dataset on the bench boxes).  Either
+data.mdb); `--wds` reads WebDataset tar shards instead (the reference's train_wds.py twin); `--synthetic` draws VAE
+moments of the configured shape (no dataset on the bench boxes).  Either
 way the moments -> latent sampling, label dropout and noise injection run as ONE fused kernel (`ops.step_front`),
 gradient accumulation (`train.grad_accum`) and the lr ramp follow train.py:211-227.
 """
@@ -61,6 +62,8 @@ def main():
     ap.add_argument("--cfg_scale", type=parse_float_none, default=None)
     ap.add_argument("--num_steps", type=int, default=40)
     ap.add_argument("--synthetic", action="store_true", help="synthetic latents instead of the LMDB dataset")
+    ap.add_argument("--wds", action="store_true",
+                    help="data.root holds WebDataset .tar shards (the reference's train_wds.py twin: lmdb2wds.py layout)")
     ap.add_argument("--max_steps", type=int, default=None, help="stop after this many steps (smoke runs)")
     args, _ = ap.parse_known_args()
     cfg = load_config(args.config)
@@ -102,6 +105,12 @@ def main():
     max_steps = args.max_steps or cfg.train.get("max_num_steps", 10 ** 9)
     if args.synthetic:
         loader = synthetic_loader(cfg, batch, device, args.global_seed + rank)
+    elif args.wds:      # train_wds.py:172-178: shards of config.data.root, split data_list[rank::world]
+        from maskdit_b200.data import wds_batches
+        shards = sorted(os.path.join(cfg.data.root, f) for f in os.listdir(cfg.data.root) if f.endswith(".tar"))
+        if rank == 0:
+            print(f"Dataset: {len(shards)} WebDataset shards ({cfg.data.root})", flush=True)
+        loader = wds_batches(shards, batch, rank, world, num_classes=cfg.model.num_classes)
     else:
         from maskdit_b200.data import ImageNetLatentDataset, batches
         ds = ImageNetLatentDataset(cfg.data.root, resolution=cfg.data.resolution, num_channels=cfg.data.num_channels,

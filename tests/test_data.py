@@ -108,3 +108,41 @@ def test_webdataset_shards_roundtrip(tmp_path):
     assert torch.equal(zb, torch.from_numpy(moments[:5])) and yb.argmax(1).tolist() == labels[:5].tolist()
     with pytest.raises(ValueError):
         next(D.wds_samples(paths[:1], rank=1, world=2))
+
+
+# ---- property tests (hypothesis): host logic against its specification over random inputs -------------------------------
+from hypothesis import given, settings, strategies as st_  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(n=st_.integers(1, 400), mb=st_.integers(1, 64), size=st_.integers(1, 8))
+def test_rank_seed_batches_equals_tensor_split(n, mb, size):
+    """sample.py:232-235 for arbitrary (seed count, max batch, world): same batches as torch.tensor_split(...)[rank::size],
+    every seed exactly once, no batch above max_batch_size, every rank the same number of batches."""
+    seeds = list(range(1000, 1000 + n))
+    num_batches = ((n - 1) // (mb * size) + 1) * size
+    ref = [b.tolist() for b in torch.as_tensor(seeds).tensor_split(num_batches)]
+    got = [rank_seed_batches(seeds, mb, r, size) for r in range(size)]
+    for r in range(size):
+        assert got[r] == ref[r::size]
+    assert sorted(s for g in got for b in g for s in b) == seeds
+    assert all(len(b) <= mb for g in got for b in g) and len({len(g) for g in got}) == 1
+
+
+@settings(max_examples=25, deadline=None)
+@given(data=st_.dictionaries(st_.binary(min_size=1, max_size=40), st_.binary(min_size=0, max_size=6000), min_size=1,
+                             max_size=120))
+def test_mdb_roundtrip_random_tables(tmp_path_factory, data):
+    """Any table of byte keys / values (inline and overflow-page values mixed) written by `write_mdb` is read back exactly
+    by the page walker, and absent keys are reported absent."""
+    d = tmp_path_factory.mktemp("mdb")
+    D.write_mdb(str(d), data)
+    rd = D.MdbReader(str(d))
+    assert rd.entries == len(data)
+    for k, v in data.items():
+        assert bytes(rd.get(k)) == v
+    for k in list(data)[:5]:
+        probe = k + b"\x00zz"
+        if probe not in data:
+            assert rd.get(probe) is None
+    rd.close()

@@ -141,7 +141,8 @@ def eval_case(name, cfg, B, num_steps=18):
     assert len(sig_seen) == 2 * num_steps - 1
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), images=images.numpy(), labels=labels.numpy(),
                         sigma=sigma.numpy(), D_plain=plain.numpy(), D_cfg=cfgout.numpy(), latents=latents.numpy(),
-                        z=z.numpy(), sampler_sigmas=np.array(sig_seen), num_steps=np.int64(num_steps))
+                        z=z.numpy(), sampler_sigmas=np.array(sig_seen),
+                        **({} if num_steps == 18 else {"num_steps": np.int64(num_steps)}))  # (s2_eval predates the key)
     print(name, "sampler |z|", z.abs().mean().item())
 
 

@@ -16,6 +16,7 @@ struct GemmParams {
   int num_m_tiles, num_n_tiles, num_kb;
   int streamk;
   int narrow_last;  // 1: the last column tile runs at half width (<= BLOCK_N/2 columns remain) - see UnitSched
+  int pair_halves;  // 1: m-major tile order, the half tiles of two adjacent m-panels form one unit - see UnitSched
   void* out;
   int ldo, out_fp32;
   const float* bias;

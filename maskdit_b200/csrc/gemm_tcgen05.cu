@@ -22,6 +22,7 @@
 // adaLN_modulation, DecoderLayer.linear, TimestepEmbedder.mlp, LabelEmbedder) and their autograd backward.
 #include "common.cuh"
 #include "gemm.h"
+#include "unit_sched.h"
 
 #include <stdlib.h>
 
@@ -59,46 +60,6 @@ struct GemmCfg {
   static constexpr int kTmemCols = (2 * BLOCK_N > 256) ? 512 : 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixed;
   static_assert(kStages >= 3, "pipeline too shallow");
-};
-
-struct UnitSched {
-  // Iterates the work units of this CTA group; identical sequence in every warp role (and in both CTAs of a pair).
-  // Units are (k-slice, tile) pairs in SLICE-major order, dealt round-robin to the groups: at any moment the resident
-  // groups work on the same k-slice of different tiles, so A/B panels are shared through L2 exactly as in a plain
-  // tiled GEMM (a tile-major stream-K order made the wgrad GEMMs DRAM-bound: every unit streamed private panels).
-  // splits == 1 is the ordinary persistent tile loop.
-  // Tile order inside a slice: when the last column tile is a half-width one (N = 1152 = 4.5 x 256: every N = 1152
-  // GEMM of the encoder, 58 % of the GEMM flops) the full-width tiles are dealt first and the half-cost tiles last,
-  // continuing the same round robin - longest-processing-time-first.  With the plain (m, n) order a CTA pair's 8-9
-  // tiles contained 1-2 half tiles at random and the makespan was 8.5 tile-times for 7.78 of work (ncu launch list r01:
-  // fc2 263 us vs 240 us for the same-flop fc1 dgrad); now it is 8.0.
-  int num_kb, num_tiles, num_n_tiles, splits, grid, n_full, full_count;
-  int unit, num_units;
-  int cur_tile, cur_m, cur_n, kb0, kb1;
-  MDT_DEVINL void init(const GemmParams& p, int cg) {
-    num_kb = p.num_kb;
-    num_n_tiles = p.num_n_tiles;
-    num_tiles = p.num_m_tiles * p.num_n_tiles;
-    splits = p.streamk;  // number of k-slices (>= 1)
-    n_full = p.narrow_last ? p.num_n_tiles - 1 : p.num_n_tiles;
-    full_count = p.num_m_tiles * n_full;
-    num_units = num_tiles * splits;
-    grid = gridDim.x / cg;
-    unit = blockIdx.x / cg;
-  }
-  MDT_DEVINL bool next() {
-    if (unit >= num_units) return false;
-    const int slice = unit / num_tiles;
-    cur_tile = unit - slice * num_tiles;
-    if (cur_tile < full_count) cur_m = cur_tile / n_full, cur_n = cur_tile - cur_m * n_full;
-    else cur_m = cur_tile - full_count, cur_n = n_full;
-    kb0 = static_cast<int>(static_cast<long long>(num_kb) * slice / splits);
-    kb1 = static_cast<int>(static_cast<long long>(num_kb) * (slice + 1) / splits);
-    unit += grid;
-    return true;
-  }
-  MDT_DEVINL int m_tile() const { return cur_m; }
-  MDT_DEVINL int n_tile() const { return cur_n; }
 };
 
 // ---- fused epilogue ---------------------------------------------------------------------------------------
@@ -421,7 +382,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t tmem_base = *tmem_base_smem;
 
   UnitSched sched;
-  sched.init(p, CG);
+  sched.init(p, CG, static_cast<int>(gridDim.x), static_cast<int>(blockIdx.x));
 
   if (warp < 4) {
   // warpgroup 0: TMA producer, MMA issuer, TMEM allocator, one idle warp.  (With > 8 epilogue warps the register file is
@@ -641,6 +602,7 @@ static int num_sms() {
 }
 
 extern int g_gemm_last_config, g_gemm_configs_seen;
+extern int g_tile_order;
 template <int BLOCK_N, bool A_MN, bool B_MN, int CG>
 static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, CG>;
@@ -683,7 +645,9 @@ static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
     }
   }
   p.streamk = splits;
-  const long long units = static_cast<long long>(tiles) * splits;
+  // tile order of the half-width last column: paired (locality, default for the non-accumulating epilogues) or LPT
+  p.pair_halves = (p.narrow_last && a.epi != EPI_ATOMIC && g_tile_order != 1) ? 1 : 0;
+  const long long units = gemm_units_per_slice(p) * splits;
   const int grid = static_cast<int>(units < groups ? units : groups) * CG;
   if (grid <= 0) return MDT_OK;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, CG>;
@@ -709,6 +673,7 @@ static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
 int g_gemm_last_config = 0;  // BLOCK_N * 10 + CG of the last launch (tests assert the 2-CTA instances ran)
 int g_gemm_configs_seen = 0;  // bit (BLOCK_N/64 - 2) * 2 + (CG - 1) per instance launched since the last reset
 static int g_force_cg = 0;  // 0 = auto, 1 / 2 = forced (MDT_GEMM_CG env, for A/B measurements)
+int g_tile_order = 0;  // half-width column tiles: 0 = paired m-major units (default), 1 = LPT (MDT_GEMM_ORDER=lpt, for A/B)
 
 template <bool A_MN, bool B_MN>
 static int dispatch_n(const mdt_gemm_args& a, cudaStream_t stream) {
@@ -716,6 +681,8 @@ static int dispatch_n(const mdt_gemm_args& a, cudaStream_t stream) {
   if (!env_read) {
     const char* e = getenv("MDT_GEMM_CG");
     if (e) g_force_cg = atoi(e);
+    const char* o = getenv("MDT_GEMM_ORDER");
+    if (o && o[0] == 'l') g_tile_order = 1;
     env_read = true;
   }
   // SM pairs (256-row tiles) whenever there are at least two 128-row panels; single CTAs for skinny problems

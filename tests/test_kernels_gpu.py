@@ -37,7 +37,9 @@ def rb(*shape, scale=1.0):
 
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,N,K", [(256, 256, 128), (512, 1152, 1152), (384, 3456, 1152), (300, 200, 1000),
-                                   (2, 1152, 256), (1024, 16, 512)])
+                                   (2, 1152, 256), (1024, 16, 512),
+                                   # half-width last column tile, paired unit order: odd panel count / several waves
+                                   (1200, 1152, 256), (20000, 1152, 128), (9000, 3456, 64)])
 def test_gemm_kk(ops, M, N, K):
     torch.manual_seed(0)
     A, B = rb(M, K), rb(N, K)
@@ -46,7 +48,8 @@ def test_gemm_kk(ops, M, N, K):
     close(out, A.float() @ B.float().t(), 1e-3, "gemm KK")
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (512, 1152, 4608), (256, 512, 16), (300, 1000, 1152)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (512, 1152, 4608), (256, 512, 16), (300, 1000, 1152),
+                                   (1200, 1152, 512)])
 def test_gemm_dgrad(ops, M, N, K):
     torch.manual_seed(1)
     A, W = rb(M, K), rb(K, N)

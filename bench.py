@@ -270,7 +270,7 @@ def run_reference_arm(args, rank):
 
 def gemm_traffic():
     """DRAM read+write bytes per GEMM launch from the committed `ncu --set full` capture (never a constant in code)."""
-    for name in ("r02_gemm_ncu_full.json", "r01_gemm_ncu_full_v3.json"):
+    for name in ("r02_gemm_ncu_full_v2.json", "r02_gemm_ncu_full.json", "r01_gemm_ncu_full_v3.json"):
         f = os.path.join(ROOT, "profiles", name)
         try:
             d = json.load(open(f))

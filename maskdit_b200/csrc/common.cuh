@@ -98,6 +98,18 @@ MDT_DEVINL void stg128(uint64_t a, float4 v) {
 MDT_DEVINL void stg64(uint64_t a, uint2 v) {
   asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(a), "r"(v.x), "r"(v.y) : "memory");
 }
+// streaming variants (evict-first in L2): epilogue traffic that is touched once must not push the GEMM's A panels out
+MDT_DEVINL void stg128_cs(uint64_t a, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+MDT_DEVINL void stg64_cs(uint64_t a, uint2 v) {
+  asm volatile("st.global.cs.v2.b32 [%0], {%1, %2};" ::"l"(a), "r"(v.x), "r"(v.y) : "memory");
+}
+MDT_DEVINL float4 ldg128_cs(uint64_t a) {
+  float4 v;
+  asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a) : "memory");
+  return v;
+}
 MDT_DEVINL float4 ldg128(uint64_t a) {
   float4 v;
   asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a) : "memory");
@@ -173,6 +185,17 @@ MDT_DEVINL void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* smem_dst,
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// L2 cache-policy operands for TMA loads (the fixed encodings CUTLASS uses, cute/arch/copy_sm90_desc.hpp)
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull, kL2EvictFirst = 0x12F0000000000000ull,
+                   kL2EvictLast = 0x14F0000000000000ull;
+MDT_DEVINL void tma_load_2d_hint(const CUtensorMap* m, uint64_t* bar, void* smem_dst, int c0, int c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+      "l"(hint)
       : "memory");
 }
 
@@ -260,6 +283,13 @@ MDT_DEVINL void tma_load_2d_2sm(const CUtensorMap* m, uint64_t* bar, void* smem_
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+MDT_DEVINL void tma_load_2d_2sm_hint(const CUtensorMap* m, uint64_t* bar, void* smem_dst, int c0, int c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
 template <int kCols>

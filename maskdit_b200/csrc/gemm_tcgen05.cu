@@ -40,6 +40,24 @@ constexpr int UMMA_K = 16;
 // tile are dealt to the kNumEpiWarps/4 warps of a lane group round robin.  With more than 8 the register file is
 // re-partitioned at kernel start (setmaxnreg: the producer/MMA warpgroup keeps 40 registers per thread).
 constexpr int kNumEpiWarps = MDT_EPI_WARPS;
+// L2 policy experiments (profiles/r02_experiments.md section 12): MDT_EPI_CS = 1 makes the epilogue's once-touched
+// global traffic (outputs, residual / GELU operand reads) evict-first; MDT_TMA_HINT = 1 loads the operand tiles with
+// the evict-last policy.
+#ifndef MDT_EPI_CS
+#define MDT_EPI_CS 0
+#endif
+#ifndef MDT_TMA_HINT
+#define MDT_TMA_HINT 0
+#endif
+#if MDT_EPI_CS
+#define MDT_STG128 stg128_cs
+#define MDT_STG64 stg64_cs
+#define MDT_LDG128 ldg128_cs
+#else
+#define MDT_STG128 stg128
+#define MDT_STG64 stg64
+#define MDT_LDG128 ldg128
+#endif
 static_assert(kNumEpiWarps % 4 == 0 && kNumEpiWarps >= 4 && kNumEpiWarps <= 16, "epilogue warps: 4, 8, 12 or 16");
 constexpr int kNumThreads = 128 + kNumEpiWarps * 32;  // 384 (8 warps) / 512 (12) / 640 (16)
 constexpr int kEpiRegs = kNumEpiWarps == 12 ? 152 : (kNumEpiWarps == 16 ? 104 : 0);  // setmaxnreg.inc target
@@ -124,7 +142,7 @@ MDT_DEVINL void epi_load(const GemmParams& p, const EpiCoord& c, int lane, EpiOp
       const uint64_t a_res = gaddr(p.resid) + (row0 * p.ld_resid + c.col) * 4, s_res = 16ull * p.ld_resid;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (4 * i + rsub < c.nrows) o.res[i] = ldg128(a_res + i * s_res);
+        if (4 * i + rsub < c.nrows) o.res[i] = MDT_LDG128(a_res + i * s_res);
     }
   }
   if constexpr (EPI == EPI_DGELU) {
@@ -160,29 +178,29 @@ MDT_DEVINL void epilogue_chunk(const GemmParams& p, uint32_t stg, const EpiCoord
       if constexpr (EPI == EPI_STORE) {
         if (p.resid) v.x += o.res[i].x, v.y += o.res[i].y, v.z += o.res[i].z, v.w += o.res[i].w;
         if (p.act == ACT_SILU) v = make_float4(silu(v.x), silu(v.y), silu(v.z), silu(v.w));
-        if (p.out_fp32) stg128(ao, v); else stg64(ao, pack4_bf16(v));
+        if (p.out_fp32) MDT_STG128(ao, v); else MDT_STG64(ao, pack4_bf16(v));
       } else if constexpr (EPI == EPI_GELU) {
         // pre-activation is rounded to bf16 first (as a bf16 nn.Linear output would be), GELU on the rounded value
         // (storing gelu'(h) here instead, so that the backward epilogue only multiplies, was measured: the forward GEMM
         // went 286 -> 333 us, the dGELU GEMM 333 -> 300 us - a net loss, profiles/r02_experiments.md section 7)
         const uint2 pre = pack4_bf16(v);
-        if (p.aux) stg64(a_aux + i * s_aux, pre);
+        if (p.aux) MDT_STG64(a_aux + i * s_aux, pre);
         const float4 h = unpack4_bf16(pre);
-        stg64(ao, pack4_bf16(make_float4(gelu_tanh(h.x), gelu_tanh(h.y), gelu_tanh(h.z), gelu_tanh(h.w))));
+        MDT_STG64(ao, pack4_bf16(make_float4(gelu_tanh(h.x), gelu_tanh(h.y), gelu_tanh(h.z), gelu_tanh(h.w))));
       } else if constexpr (EPI == EPI_GATE_RESID) {
-        if (p.aux) stg64(a_aux + i * s_aux, pack4_bf16(v));
+        if (p.aux) MDT_STG64(a_aux + i * s_aux, pack4_bf16(v));
         float4 g = o.gate4;
         if (!o.gate_uniform) {
           const size_t b = (row0 + 4 * i) / p.rows_per_group;
           g = ldg128_nc(gaddr(p.gate + b * p.ld_gate + c.col));
         }
         const float4 r = o.res[i];  // may alias `out` (in-place residual update): each element is read before written
-        stg128(ao, make_float4(fmaf(g.x, v.x, r.x), fmaf(g.y, v.y, r.y), fmaf(g.z, v.z, r.z), fmaf(g.w, v.w, r.w)));
+        MDT_STG128(ao, make_float4(fmaf(g.x, v.x, r.x), fmaf(g.y, v.y, r.y), fmaf(g.z, v.z, r.z), fmaf(g.w, v.w, r.w)));
       } else if constexpr (EPI == EPI_DGELU) {
         const float4 h = unpack4_bf16(o.auxv[i]);
         const uint2 ov = pack4_bf16(make_float4(v.x * gelu_tanh_grad(h.x), v.y * gelu_tanh_grad(h.y),
                                                 v.z * gelu_tanh_grad(h.z), v.w * gelu_tanh_grad(h.w)));
-        stg64(ao, ov);
+        MDT_STG64(ao, ov);
         const float4 r = unpack4_bf16(ov);  // sum what was stored (what a separate column-sum pass would read back)
         cs.x += r.x, cs.y += r.y, cs.z += r.z, cs.w += r.w;
       }
@@ -407,8 +425,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
         const int k0 = kb * BLOCK_K;
         auto load = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
+#if MDT_TMA_HINT
+          if constexpr (CG == 2) tma_load_2d_2sm_hint(m, &full_bar[stage], dst, c0, c1, kL2EvictLast);
+          else tma_load_2d_hint(m, &full_bar[stage], dst, c0, c1, kL2EvictLast);
+#else
           if constexpr (CG == 2) tma_load_2d_2sm(m, &full_bar[stage], dst, c0, c1);
           else tma_load_2d(m, &full_bar[stage], dst, c0, c1);
+#endif
         };
         if constexpr (!A_MN) {
           load(&tmap_a, sa, k0, m0);  // box {64 k, 128 rows}

@@ -102,7 +102,8 @@ def main():
     ratio_fn = mask_ratio_schedule(cfg.model.get("mask_ratio_fn", "constant"), cfg.model.mask_ratio,
                                    cfg.model.get("mask_ratio_min", 0) or 0)
     drop = cfg.model.get("class_dropout_prob", 0) or 0
-    max_steps = args.max_steps or cfg.train.get("max_num_steps", 10 ** 9)
+    cfg_max_steps = cfg.train.get("max_num_steps", None) or 10 ** 9
+    max_steps = args.max_steps or cfg_max_steps        # --max_steps only shortens the run (smoke runs) ...
     if args.synthetic:
         loader = synthetic_loader(cfg, batch, device, args.global_seed + rank)
     elif args.wds:      # train_wds.py:172-178: shards of config.data.root, split data_list[rank::world]
@@ -123,7 +124,7 @@ def main():
     for moments, labels in loader:
         moments = moments.to(device, non_blocking=True)
         labels = labels.to(device, non_blocking=True)
-        ratio = ratio_fn((step - step0) / max_steps)
+        ratio = ratio_fn((step - step0) / cfg_max_steps)   # ... the schedule keeps the config's horizon (train.py:208)
         # moments -> latent (train.py:206), label dropout (:209), noise injection (loss.py:35-39): fused step front
         loss = ts.step(moments, labels, ratio, cfg.model.mae_loss_coef, grad_accum=rounds, moments=True,
                        class_dropout_prob=drop)

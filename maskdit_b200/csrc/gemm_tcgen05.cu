@@ -625,7 +625,7 @@ static int num_sms() {
 }
 
 extern int g_gemm_last_config, g_gemm_configs_seen;
-extern int g_tile_order;
+extern int g_tile_order, g_split_rule;
 template <int BLOCK_N, bool A_MN, bool B_MN, int CG>
 static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, CG>;
@@ -653,10 +653,14 @@ static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
   p.colsum = a.epi == EPI_DGELU ? a.colsum : nullptr;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int groups = num_sms() / CG;  // CTA groups resident at once (1 CTA per SM)
-  // k-slices: only for the accumulate epilogue (fp32 red.add).  Pick the smallest slice count whose unit count
-  // fills >= 90 % of the last wave; each extra slice costs one more tile-sized pass of L2 reductions.
+  // k-slices: only for the accumulate epilogue (fp32 red.add).  Units = tiles x slices are dealt round robin to the
+  // CTA groups, so a launch lasts ceil(units / groups) unit-times; a unit costs its k-blocks plus a fixed part (pipeline
+  // fill, the exposed share of the tile's reduction epilogue: ~4 k-blocks' worth).  Pick the slice count that minimises
+  // waves x (num_kb / slices + 4).  (The first rule took the smallest of {1,2,3,4,6,8,12,16,32} slices that filled
+  // >= 90 % of the last wave: 3 slices for the 90-tile fc1 / fc2 wgrads = 270 units on 74 pairs = 4 waves of 171
+  // k-blocks, where 4 slices give 5 waves of 128: -6 %; MDT_GEMM_SPLITS=r1 keeps that rule for A/B.)
   int splits = 1;
-  if (a.epi == EPI_ATOMIC) {
+  if (a.epi == EPI_ATOMIC && g_split_rule == 1) {
     double best_eff = 0.0;
     const int cand[9] = {1, 2, 3, 4, 6, 8, 12, 16, 32};
     for (int c : cand) {
@@ -665,6 +669,13 @@ static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
       const double eff = static_cast<double>(u) / (static_cast<double>((u + groups - 1) / groups) * groups);
       if (eff > best_eff + 0.03) best_eff = eff, splits = c;
       if (eff >= 0.9) break;
+    }
+  } else if (a.epi == EPI_ATOMIC) {
+    double best = 0.0;
+    for (int c = 1; c <= 32 && c <= p.num_kb; ++c) {
+      const long long u = static_cast<long long>(tiles) * c;
+      const double t = static_cast<double>((u + groups - 1) / groups) * (static_cast<double>(p.num_kb) / c + 4.0);
+      if (c == 1 || t < best * 0.995) best = t, splits = c;  // ties and near-ties go to fewer slices (fewer reductions)
     }
   }
   p.streamk = splits;
@@ -697,6 +708,7 @@ int g_gemm_last_config = 0;  // BLOCK_N * 10 + CG of the last launch (tests asse
 int g_gemm_configs_seen = 0;  // bit (BLOCK_N/64 - 2) * 2 + (CG - 1) per instance launched since the last reset
 static int g_force_cg = 0;  // 0 = auto, 1 / 2 = forced (MDT_GEMM_CG env, for A/B measurements)
 int g_tile_order = 0;  // half-width column tiles: 0 = paired m-major units (default), 1 = LPT (MDT_GEMM_ORDER=lpt, for A/B)
+int g_split_rule = 0;  // k-slices of the accumulating GEMMs: 0 = wave-time model (default), 1 = round-1 rule (MDT_GEMM_SPLITS=r1)
 
 template <bool A_MN, bool B_MN>
 static int dispatch_n(const mdt_gemm_args& a, cudaStream_t stream) {
@@ -706,6 +718,8 @@ static int dispatch_n(const mdt_gemm_args& a, cudaStream_t stream) {
     if (e) g_force_cg = atoi(e);
     const char* o = getenv("MDT_GEMM_ORDER");
     if (o && o[0] == 'l') g_tile_order = 1;
+    const char* sr = getenv("MDT_GEMM_SPLITS");
+    if (sr && sr[0] == 'r') g_split_rule = 1;
     env_read = true;
   }
   // SM pairs (256-row tiles) whenever there are at least two 128-row panels; single CTAs for skinny problems

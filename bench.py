@@ -379,11 +379,12 @@ def main():
             torch.cuda.empty_cache()
 
             def c4():
-                net64 = build_xl2(64, dev)
+                net64 = None
                 try:
+                    net64 = build_xl2(64, dev)
                     return bench_train(args, net64, env, 64, PK, 128, max(4, args.steps // 4), 3, full=False)
                 finally:
-                    del net64
+                    net64 = None
                     torch.cuda.empty_cache()
 
             guarded("c4_512px", c4)

@@ -73,6 +73,11 @@ typedef struct mdt_gemm_args {
 } mdt_gemm_args;
 
 int mdt_gemm_bf16(const mdt_gemm_args* args, void* stream);
+/* The host-side decisions mdt_gemm_bf16 would take for `args`, without launching anything (needs no device: host
+ * tests pin the dispatch with it; pointers in `args` are only checked for alignment, never dereferenced):
+ * out10 = {BLOCK_N, CTAs per tile (2 = cta_group::2 SM pair), k-slices, paired half-tile order (0/1), half-width last
+ * column tile (0/1), row tiles, column tiles, k-blocks of 64, work units, grid size in CTAs}.                        */
+int mdt_gemm_plan(const mdt_gemm_args* args, long long* out10);
 /* Measurement aid (bench.py roofline): while enabled, every mdt_gemm_bf16 launch of this process - also the step
  * driver's - is bracketed by CUDA events on its stream; mdt_gemm_profile_read returns the launch count and fills
  * ms[i] (device time) / flops[i] (2 M N K) for i < cap.  Enabling clears the previous recording.                   */

@@ -58,6 +58,7 @@ _lib = None
 _P, _I, _F, _LL, _D = c_void_p, c_int, c_float, c_longlong, c_double
 _SIGS = {
     "mdt_gemm_bf16": [POINTER(GemmArgs), _P],
+    "mdt_gemm_plan": [POINTER(GemmArgs), _P],
     "mdt_gemm_profile_enable": [_I],
     "mdt_gemm_profile_read": [_P, _P, _I],
     "mdt_mask_indices": [_P, _I, _I, _I, _P, _P, _P, _P],
@@ -169,6 +170,28 @@ def _req_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
             raise MdtError("maskdit_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+PLAN_FIELDS = ("block_n", "cg", "splits", "pair_halves", "narrow_last", "num_m_tiles", "num_n_tiles", "num_kb", "units",
+               "grid")
+
+
+def gemm_plan(M, N, K, *, a_mn=False, b_mn=False, epi=EPI_STORE, block_n=0):
+    """The host-side decisions `mdt_gemm_bf16` takes for this problem (tile width, SM pairs, k-slices, unit order,
+    grid), without a launch or a device: `mdt_gemm_plan`.  Operand pointers are dummies (checked for alignment only)."""
+    a = GemmArgs()
+    a.A = a.B = a.out = a.aux = a.resid = a.gate = 4096
+    a.M, a.N, a.K = M, N, K
+    a.lda, a.ldb, a.ldo = (M if a_mn else K), (N if b_mn else K), N
+    a.a_mn, a.b_mn, a.epi, a.act = int(a_mn), int(b_mn), epi, ACT_NONE
+    a.out_fp32 = int(epi in (EPI_ATOMIC, EPI_GATE_RESID))
+    a.ld_aux = a.ld_resid = a.ld_gate = N
+    a.rows_per_group, a.block_n = 1, block_n
+    out = (c_longlong * 10)()
+    st = lib().mdt_gemm_plan(ctypes.byref(a), out)
+    if st != 0:
+        raise MdtError(f"mdt_gemm_plan failed: {lib().mdt_status_string(st).decode()} (status {st})")
+    return dict(zip(PLAN_FIELDS, (int(v) for v in out)))
 
 
 def gemm(A, B, M, N, K, *, lda=None, ldb=None, a_mn=False, b_mn=False, epi=EPI_STORE, act=ACT_NONE, out=None,

@@ -73,6 +73,17 @@ int mdt_gemm_profile_read(float* ms, double* flops, int cap) {
   return n;
 }
 
+int mdt_gemm_plan(const mdt_gemm_args* args, long long* out10) {
+  if (!args || !out10) return MDT_ERR_ARG;
+  mdt::GemmPlan pl;
+  const int rc = mdt::gemm_plan(*args, &pl);
+  if (rc != MDT_OK) return rc;
+  const long long v[10] = {pl.block_n, pl.cg, pl.splits, pl.pair_halves, pl.narrow_last,
+                           pl.num_m_tiles, pl.num_n_tiles, pl.num_kb, pl.units, pl.grid};
+  for (int i = 0; i < 10; ++i) out10[i] = v[i];
+  return MDT_OK;
+}
+
 int mdt_gemm_bf16(const mdt_gemm_args* args, void* stream) {
   if (!args || !args->A || !args->B || !args->out) return MDT_ERR_ARG;
   if (!g_probe_on) return mdt::gemm_launch(*args, static_cast<cudaStream_t>(stream));

@@ -31,6 +31,14 @@ struct GemmParams {
 
 int gemm_launch(const mdt_gemm_args& a, cudaStream_t stream);
 
+// Host-side decisions of one launch (tile width, CTAs per tile, k-slices, unit order, grid) - what mdt_gemm_plan reports.
+struct GemmPlan {
+  int block_n, cg, splits, pair_halves, narrow_last, num_m_tiles, num_n_tiles, num_kb;
+  long long units;
+  int grid;
+};
+int gemm_plan(const mdt_gemm_args& a, GemmPlan* out);
+
 // Tensor map that makes TMA write attention token tiles directly in the UMMA no-swizzle core-matrix layout
 // (attention_tc.cuh): a row-major bf16 matrix [rows, row_elems] is described as the 4-D tensor
 // {8 elements (16 B), 8 rows, row_elems/8 chunks, rows/8 row blocks}; a box {8, 8, chunks, row_blocks} lands in smem as

@@ -626,18 +626,11 @@ static int num_sms() {
 
 extern int g_gemm_last_config, g_gemm_configs_seen;
 extern int g_tile_order, g_split_rule;
+static thread_local GemmPlan* g_plan_out = nullptr;  // set by gemm_plan() around a gemm_launch() call
 template <int BLOCK_N, bool A_MN, bool B_MN, int CG>
 static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, CG>;
   constexpr int TILE_M = BLOCK_M * CG;
-  CUtensorMap ta, tb;
-  int rc;
-  // A: K-major stored [M, K] ld=lda -> dims {K, M}, box {64, 128}; MN-major stored [K, M] -> dims {M, K}, box {64, 64}
-  rc = A_MN ? make_tmap(&ta, a.A, a.M, a.K, a.lda, 64, 64) : make_tmap(&ta, a.A, a.K, a.M, a.lda, 64, BLOCK_M);
-  if (rc) return rc;
-  rc = B_MN ? make_tmap(&tb, a.B, a.N, a.K, a.ldb, 64, 64) : make_tmap(&tb, a.B, a.K, a.N, a.ldb, 64, Cfg::kBRows);
-  if (rc) return rc;
-
   GemmParams p;
   p.M = a.M, p.N = a.N, p.K = a.K;
   p.epi = a.epi, p.act = a.act;
@@ -683,7 +676,19 @@ static int launch(const mdt_gemm_args& a, cudaStream_t stream) {
   p.pair_halves = (p.narrow_last && a.epi != EPI_ATOMIC && g_tile_order != 1) ? 1 : 0;
   const long long units = gemm_units_per_slice(p) * splits;
   const int grid = static_cast<int>(units < groups ? units : groups) * CG;
+  if (g_plan_out) {  // mdt_gemm_plan: report the decisions, launch nothing (no device, no driver needed)
+    *g_plan_out = GemmPlan{BLOCK_N, CG, splits, p.pair_halves, p.narrow_last, p.num_m_tiles, p.num_n_tiles, p.num_kb,
+                           units, grid};
+    return MDT_OK;
+  }
   if (grid <= 0) return MDT_OK;
+  CUtensorMap ta, tb;
+  int rc;
+  // A: K-major stored [M, K] ld=lda -> dims {K, M}, box {64, 128}; MN-major stored [K, M] -> dims {M, K}, box {64, 64}
+  rc = A_MN ? make_tmap(&ta, a.A, a.M, a.K, a.lda, 64, 64) : make_tmap(&ta, a.A, a.K, a.M, a.lda, 64, BLOCK_M);
+  if (rc) return rc;
+  rc = B_MN ? make_tmap(&tb, a.B, a.N, a.K, a.ldb, 64, 64) : make_tmap(&tb, a.B, a.K, a.N, a.ldb, 64, Cfg::kBRows);
+  if (rc) return rc;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -762,6 +767,15 @@ int gemm_launch(const mdt_gemm_args& a, cudaStream_t stream) {
   if (!a.a_mn && a.b_mn) return dispatch_n<false, true>(a, stream);
   if (!a.a_mn && !a.b_mn) return dispatch_n<false, false>(a, stream);
   return MDT_ERR_ARG;  // (MN, K) is never needed by this path
+}
+
+int gemm_plan(const mdt_gemm_args& a, GemmPlan* out) {
+  GemmPlan pl = {};
+  g_plan_out = &pl;
+  const int rc = gemm_launch(a, nullptr);
+  g_plan_out = nullptr;
+  if (rc == MDT_OK && out) *out = pl;
+  return rc;
 }
 
 }  // namespace mdt

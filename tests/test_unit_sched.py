@@ -6,6 +6,7 @@ N = 1152 GEMMs of the XL/2 encoder (4.5 column tiles of 256) the paired order ha
 (8 tile-times on 74 SM pairs) while an m-panel's column tiles stay within adjacent waves (L2 locality of the A panel).
 """
 import os
+import shutil
 import subprocess
 
 import pytest
@@ -15,6 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def checker(tmp_path_factory):
+    if shutil.which("g++") is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("needs g++ and the CUDA headers (gemm.h includes cuda_runtime.h)")
     exe = str(tmp_path_factory.mktemp("usc") / "unit_sched_check")
     subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "maskdit_b200", "csrc"),
                     "-I", "/usr/local/cuda/include", os.path.join(ROOT, "tests", "host", "unit_sched_check.cpp"),
